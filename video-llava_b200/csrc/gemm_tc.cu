@@ -1,0 +1,389 @@
+// Dense bf16 GEMM on the 5th-generation tensor cores:  C[M,N] = epilogue(A[M,K] . W[N,K]^T)
+//
+// This one kernel serves every dense contraction on the hot path (SURVEY.md section 2.3 rows
+// V1, V3, V5-V7, J1, L1, L4-L6): both operands are K-major exactly as nn.Linear stores them
+// (activations [rows, K], weights [out, in]), so no transposes are ever materialised.
+//
+//   warp 0      TMA producer : cp.async.bulk.tensor 2-D tiles (128B swizzle) -> smem ring
+//   warp 1      MMA issuer   : one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage
+//   warp 2      TMEM allocator (2 accumulator buffers of BLOCK_N fp32 columns)
+//   warps 4-7   epilogue     : tcgen05.ld 32 lanes x 32 columns -> bias / activation / residual
+//                              -> bf16 -> global (64 B contiguous per thread per chunk)
+//
+// Persistent: grid = min(#tiles, #SMs); the accumulator is double-buffered in TMEM so the
+// epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// Rounding points reproduce the reference's eager bf16 path (each nn.Linear output is rounded to
+// bf16 before the following elementwise op):
+//   CLIP quick_gelu  x*sigmoid(1.702x)   transformers/activations.py:117-123
+//   CLIP residual    hidden + out        transformers/models/clip/modeling_clip.py:377,382
+//   LLaMA SwiGLU     silu(gate)*up       transformers/models/llama/modeling_llama.py:182-184
+//   LLaMA residual                       transformers/models/llama/modeling_llama.py:325,331
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cudaTypedefs.h>
+
+namespace vcl {
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle span
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual align
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "tmem");
+  static_assert((2 * STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier area");
+};
+
+__device__ __forceinline__ float act_quick_gelu(float x) {
+  // three bf16 tensors are materialised by the reference: 1.702*x, sigmoid(.), x*sigmoid(.)
+  x = bf16r(x);
+  float t = bf16r(1.702f * x);
+  float s = bf16r(1.0f / (1.0f + __expf(-t)));
+  return x * s;
+}
+__device__ __forceinline__ float act_gelu_erf(float x) {
+  x = bf16r(x);
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+__device__ __forceinline__ float act_silu(float g) {
+  g = bf16r(g);
+  return bf16r(g / (1.0f + __expf(-g)));
+}
+
+template <int BLOCK_N, int ACT>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, bf16* C, long long ldc,
+                    const bf16* __restrict__ bias, const bf16* residual, long long ldr, int M,
+                    int N, int K) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = smem_raw + pad;                 // 1024-byte aligned (SWIZZLE_128B atoms)
+  const uint32_t smem_base = raw_addr + pad;
+
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), Cfg::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_m = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * Cfg::BLOCK_K, m_blk * Cfg::BLOCK_M);
+          tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_b, full_bar(stage), kb * Cfg::BLOCK_K,
+                      n_blk * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(Cfg::BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase);          // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_k_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr >> 4) field
+            tc_mma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));                // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));                    // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 4;                          // == warp % 4: TMEM lane quarter of this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * Cfg::BLOCK_M + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
+        tmem_ld_32x32(taddr + c * 32, v);
+        tc_wait_ld();
+        if (c == BLOCK_N / 32 - 1) {
+          // every TMEM read of this accumulator has completed: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (!row_ok || col0 >= N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (bias != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 b = *reinterpret_cast<const uint4*>(bias + col0 + q * 8);
+            f[q * 8 + 0] += bf16lo(b.x); f[q * 8 + 1] += bf16hi(b.x);
+            f[q * 8 + 2] += bf16lo(b.y); f[q * 8 + 3] += bf16hi(b.y);
+            f[q * 8 + 4] += bf16lo(b.z); f[q * 8 + 5] += bf16hi(b.z);
+            f[q * 8 + 6] += bf16lo(b.w); f[q * 8 + 7] += bf16hi(b.w);
+          }
+        }
+        if constexpr (ACT == ACT_SWIGLU) {
+          // weight rows are interleaved (2j = gate_j, 2j+1 = up_j): 32 columns -> 16 outputs
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float y0 = act_silu(f[4 * j + 0]) * bf16r(f[4 * j + 1]);
+            const float y1 = act_silu(f[4 * j + 2]) * bf16r(f[4 * j + 3]);
+            o[j] = pack_bf16x2(y0, y1);
+          }
+          bf16* dst = C + (long long)row * ldc + (col0 >> 1);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+          if constexpr (ACT == ACT_QGELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = act_quick_gelu(f[j]);
+          } else if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = act_gelu_erf(f[j]);
+          }
+          if (residual != nullptr) {
+            const bf16* rsrc = residual + (long long)row * ldr + col0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 r = *reinterpret_cast<const uint4*>(rsrc + q * 8);
+              f[q * 8 + 0] = bf16r(f[q * 8 + 0]) + bf16lo(r.x);
+              f[q * 8 + 1] = bf16r(f[q * 8 + 1]) + bf16hi(r.x);
+              f[q * 8 + 2] = bf16r(f[q * 8 + 2]) + bf16lo(r.y);
+              f[q * 8 + 3] = bf16r(f[q * 8 + 3]) + bf16hi(r.y);
+              f[q * 8 + 4] = bf16r(f[q * 8 + 4]) + bf16lo(r.z);
+              f[q * 8 + 5] = bf16r(f[q * 8 + 5]) + bf16hi(r.z);
+              f[q * 8 + 6] = bf16r(f[q * 8 + 6]) + bf16lo(r.w);
+              f[q * 8 + 7] = bf16r(f[q * 8 + 7]) + bf16hi(r.w);
+            }
+          }
+          bf16* dst = C + (long long)row * ldc + col0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+            o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+            o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+            o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(dst + q * 8) = o;
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int resolve_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the driver (%s)",
+                   cudaGetErrorString(e));
+    return -2;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return 0;
+}
+
+// 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle.
+static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long long cols,
+                     long long ld, int box_rows) {
+  if (resolve_encode() != 0) return -2;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%lld cols=%lld ld=%lld box=%d",
+                   (int)r, ptr, rows, cols, ld, box_rows);
+    return -2;
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+int device_num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BLOCK_N, int ACT>
+static int launch_one(const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, ACT>;
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, g.A, g.M, g.K, g.lda, Cfg::BLOCK_M) != 0) return -2;
+  if (make_tmap(&tb, g.W, g.N, g.K, g.ldw, BLOCK_N) != 0) return -2;
+  const int num_tiles = ((g.M + 127) / 128) * ((g.N + BLOCK_N - 1) / BLOCK_N);
+  int grid = num_tiles < device_num_sms() ? num_tiles : device_num_sms();
+  if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
+  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, g.C, g.ldc, g.bias, g.residual, g.ldr, g.M,
+                                              g.N, g.K);
+  VCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int BLOCK_N>
+static int launch_act(const GemmArgs& g, cudaStream_t stream) {
+  switch (g.act) {
+    case ACT_NONE: return launch_one<BLOCK_N, ACT_NONE>(g, stream);
+    case ACT_QGELU: return launch_one<BLOCK_N, ACT_QGELU>(g, stream);
+    case ACT_GELU: return launch_one<BLOCK_N, ACT_GELU>(g, stream);
+    case ACT_SWIGLU: return launch_one<BLOCK_N, ACT_SWIGLU>(g, stream);
+  }
+  set_last_error("gemm: unknown activation %d", g.act);
+  return -1;
+}
+
+template <int BLOCK_N, int ACT>
+static int init_one() {
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, ACT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   GemmCfg<BLOCK_N>::SMEM_BYTES));
+  return 0;
+}
+template <int BLOCK_N>
+static int init_bn() {
+  if (init_one<BLOCK_N, ACT_NONE>() || init_one<BLOCK_N, ACT_QGELU>() ||
+      init_one<BLOCK_N, ACT_GELU>() || init_one<BLOCK_N, ACT_SWIGLU>()) return -2;
+  return 0;
+}
+// Opt every instantiation into its dynamic shared memory size (done once, outside any capture).
+int init_gemm_kernels() {
+  if (resolve_encode() != 0) return -2;
+  if (init_bn<256>() || init_bn<128>() || init_bn<64>() || init_bn<32>()) return -2;
+  return 0;
+}
+
+int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
+  VCL_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  VCL_REQUIRE(g.K % 64 == 0, "gemm: K=%d must be a multiple of 64", g.K);
+  VCL_REQUIRE(g.N % 32 == 0, "gemm: N=%d must be a multiple of 32", g.N);
+  VCL_REQUIRE(g.lda % 8 == 0 && g.ldw % 8 == 0 && g.ldc % 8 == 0, "gemm: pitches must be x8");
+  VCL_REQUIRE(((uintptr_t)g.A % 16) == 0 && ((uintptr_t)g.W % 16) == 0 &&
+                  ((uintptr_t)g.C % 16) == 0, "gemm: pointers must be 16-byte aligned");
+  VCL_REQUIRE(g.residual == nullptr || (g.ldr % 8 == 0 && ((uintptr_t)g.residual % 16) == 0),
+              "gemm: residual must be 16-byte aligned with pitch x8");
+  VCL_REQUIRE(g.bias == nullptr || ((uintptr_t)g.bias % 16) == 0, "gemm: bias alignment");
+  VCL_REQUIRE(!(g.act == ACT_SWIGLU && g.residual != nullptr), "gemm: swiglu takes no residual");
+  int bn = g.block_n;
+  if (bn == 0) {
+    // pick the widest tile that still gives every SM at least one tile (wave quantisation)
+    const int sms = device_num_sms();
+    const long long mt = (g.M + 127) / 128;
+    bn = 256;
+    while (bn > 32 && (g.N % bn != 0 || mt * (g.N / bn) < sms)) bn >>= 1;
+    if (g.N % bn != 0) bn = 32;
+  }
+  switch (bn) {
+    case 256: return launch_act<256>(g, stream);
+    case 128: return launch_act<128>(g, stream);
+    case 64: return launch_act<64>(g, stream);
+    case 32: return launch_act<32>(g, stream);
+  }
+  set_last_error("gemm: unsupported block_n %d", bn);
+  return -1;
+}
+
+}  // namespace vcl

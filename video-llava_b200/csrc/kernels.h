@@ -1,0 +1,109 @@
+// Internal launcher prototypes shared between the kernel translation units and vcl_api.cu.
+// Everything here enqueues on the stream it is given and never synchronises.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vcl {
+
+typedef __nv_bfloat16 bf16;
+
+enum Act { ACT_NONE = 0, ACT_QGELU = 1, ACT_GELU = 2, ACT_SWIGLU = 3 };
+
+void set_last_error(const char* fmt, ...);
+int device_num_sms();
+
+// ---- gemm_tc.cu : C[M,N] = epi(A[M,K] . W[N,K]^T), tcgen05 + TMA -------------------------------
+struct GemmArgs {
+  const bf16* A = nullptr;  long long lda = 0;   // activations, row pitch in elements
+  const bf16* W = nullptr;  long long ldw = 0;   // weights [N,K] (nn.Linear layout)
+  bf16* C = nullptr;        long long ldc = 0;   // output (width N, or N/2 for ACT_SWIGLU)
+  const bf16* bias = nullptr;                    // [N] or null
+  const bf16* residual = nullptr; long long ldr = 0;  // [M,N] or null; may alias C
+  int M = 0, N = 0, K = 0;
+  int act = ACT_NONE;
+  int block_n = 0;     // 0 = choose
+  int max_ctas = 0;    // 0 = one per SM
+};
+int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
+int init_gemm_kernels();
+
+// ---- elementwise.cu ---------------------------------------------------------------------------
+// y = LayerNorm(x) * w + b   (rows x D, fp32 statistics, one bf16 rounding)
+int launch_layernorm(const bf16* x, long long ldx, bf16* y, long long ldy, const bf16* w,
+                     const bf16* b, int rows, int D, float eps, cudaStream_t stream);
+// y = w * bf16(x * rsqrt(mean(x^2)+eps))   (LlamaRMSNorm rounding order)
+int launch_rmsnorm(const bf16* x, long long ldx, bf16* y, long long ldy, const bf16* w, int rows,
+                   int D, float eps, cudaStream_t stream);
+// pixels -> patch matrix [N*P, KP] (k = c*ps*ps + i*ps + j, zero padded to KP)
+//   mode 0: bf16 NCHW already normalised;  mode 1: uint8 NHWC raw, CLIP mean/std applied here
+int launch_im2col(const void* pixels, int mode, bf16* out, int n_frames, int image, int patch,
+                  int KP, cudaStream_t stream);
+// h[n, 0] = LN(cls + pos[0]); h[n, 1+p] = LN(patch[n*P+p] + pos[1+p])
+int launch_clip_embed_ln(const bf16* patch_out, const bf16* cls, const bf16* pos, const bf16* ln_w,
+                         const bf16* ln_b, bf16* h, int n_frames, int P, int D, float eps,
+                         cudaStream_t stream);
+// token-embedding gather with the projected video rows spliced in after <vid_start>
+int launch_embed_splice(const long long* ids, const bf16* table, const bf16* vid, const int* vid_start,
+                        bf16* h, int B, int S, int D, int n_vid, int vocab, cudaStream_t stream);
+// cos/sin tables [max_pos, head_dim/2] rounded to bf16 (stored as bf16)
+int launch_rope_table(bf16* cos_t, bf16* sin_t, int max_pos, int head_dim, float theta,
+                      cudaStream_t stream);
+// prefill: rotate q (in place inside qkv) and k, write k/v into the cache at [pos0, pos0+S)
+int launch_rope_kv_prefill(bf16* qkv, bf16* kcache, bf16* vcache, const bf16* cos_t,
+                           const bf16* sin_t, int B, int S, int H, int head_dim, int s_max, int pos0,
+                           cudaStream_t stream);
+// h[b,:] = table[tok[b*tok_stride]]  (decode-time embedding lookup, tokens live on the device)
+int launch_embed_tokens(const int* tok, long long tok_stride, const bf16* table, bf16* h, int B,
+                        int D, int vocab, cudaStream_t stream);
+int launch_argmax(const float* logits, int* out, long long out_stride, int B, int V,
+                  cudaStream_t stream);
+
+// ---- st_pool.cu ---------------------------------------------------------------------------------
+// dtype codes: 0 = fp16, 1 = bf16
+int launch_st_pool(const void* feats, int in_dtype, long long frame_stride, long long patch_stride,
+                   int T, int P, int C, int n_temporal, void* out, int out_dtype,
+                   cudaStream_t stream);
+
+// ---- attention.cu -------------------------------------------------------------------------------
+// softmax(Q K^T * scale [+ causal]) V for S_q == S_kv, bf16, fp32 softmax; element (b,h,s,d) of
+// each operand lives at base + b*sb + h*sh + s*ss + d.
+struct AttnArgs {
+  const bf16* q; long long q_sb, q_sh, q_ss;
+  const bf16* k; long long k_sb, k_sh, k_ss;
+  const bf16* v; long long v_sb, v_sh, v_ss;
+  bf16* o;       long long o_sb, o_sh, o_ss;
+  int B, H, S, head_dim;
+  float scale;
+  int causal;
+};
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+int init_attention_kernels();
+// single-query attention against the cache: q [B, H*hd] -> o [B, H*hd]; kv_len keys per clip
+int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, const bf16* vcache,
+                            bf16* o, long long o_ld, int B, int H, int head_dim, int s_max,
+                            int kv_len, float scale, cudaStream_t stream);
+
+// ---- gemv.cu : decode-time weight streaming (M = B <= 8 rows) ------------------------------------
+struct GemvArgs {
+  const bf16* x = nullptr; long long ldx = 0;   // [B, K]
+  const bf16* W = nullptr;                      // [N, K]
+  int B = 0, N = 0, K = 0;
+  const bf16* norm_w = nullptr; float eps = 0;  // optional fused RMSNorm prologue
+};
+// out[b, n] = bf16(bf16(x.W[n]) + res[b, n])      (res may alias out; res == null -> plain)
+int launch_gemv_residual(const GemvArgs& g, bf16* out, long long ldo, const bf16* res,
+                         long long ldr, cudaStream_t stream);
+// W rows interleaved (2j gate, 2j+1 up): out[b, j] = silu(gate)*up,  N = 2*F
+int launch_gemv_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t stream);
+// fused q/k/v projection + RoPE + cache write for one new token per clip at position pos
+int launch_gemv_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
+                         const bf16* cos_t, const bf16* sin_t, int H, int head_dim, int s_max,
+                         int pos, cudaStream_t stream);
+int init_gemv_kernels();
+// logits (bf16-rounded, stored fp32) [B, N]
+int launch_gemv_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
+
+}  // namespace vcl

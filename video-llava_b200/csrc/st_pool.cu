@@ -1,0 +1,132 @@
+// Spatio-temporal mean pool: patch features [T, P, C] -> [n_temporal + P, C] video tokens.
+//
+// Reference: video_chatgpt/inference.py:13-44 (get_spatio_temporal_features_torch) and the numpy
+// twin scripts/save_spatio_temporal_clip_features.py:46-57:
+//   rows 0..T-1            mean over the P patches of frame t       ("temporal" tokens)
+//   rows T..n_temporal-1   zeros (only when T < n_temporal)
+//   rows n_temporal..      mean over the T frames of patch p        ("spatial" tokens)
+// torch.mean accumulates in fp32 and rounds to the input dtype; the reference then casts the
+// concatenation to fp16 (`.half()`), so the result is round_out(round_in(fp32 mean)).
+//
+// HBM-bound: 2*T*P*C bytes in, (n_temporal+P)*C*2 out (52.4 MB / 0.73 MB at T=100, P=256).
+// One launch, two CTA roles, no atomics and a fixed summation order (deterministic):
+//   blockIdx <  T        temporal role: CTA walks the P patch rows of one frame
+//   blockIdx >= T        spatial  role: CTA walks the T frames of one patch row
+// Every thread owns 8 consecutive channels (one 128-bit load per row) and keeps UNROLL loads in
+// flight; both roles stream the same tensor concurrently so the second touch of a line is an L2
+// hit rather than a second HBM read.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vcl {
+
+namespace {
+
+template <bool IN_BF16>
+__device__ __forceinline__ void acc8(const uint4& u, float* a) {
+  if (IN_BF16) {
+    a[0] += bf16lo(u.x); a[1] += bf16hi(u.x); a[2] += bf16lo(u.y); a[3] += bf16hi(u.y);
+    a[4] += bf16lo(u.z); a[5] += bf16hi(u.z); a[6] += bf16lo(u.w); a[7] += bf16hi(u.w);
+  } else {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      a[2 * j] += f.x;
+      a[2 * j + 1] += f.y;
+    }
+  }
+}
+
+template <bool IN_BF16, bool OUT_BF16>
+__device__ __forceinline__ uint32_t round_pair(float x, float y) {
+  // round to the input dtype first (torch.mean's result dtype), then to the output dtype
+  if (IN_BF16) { x = bf16r(x); y = bf16r(y); }
+  else { x = __half2float(__float2half_rn(x)); y = __half2float(__float2half_rn(y)); }
+  if (OUT_BF16) return pack_bf16x2(x, y);
+  __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <bool IN_BF16, bool OUT_BF16>
+__global__ void __launch_bounds__(128)
+st_pool_kernel(const uint16_t* __restrict__ feats, long long frame_stride, long long patch_stride,
+               int T, int P, int C, int n_temporal, uint16_t* __restrict__ out) {
+  constexpr int UNROLL = 8;
+  const int c0 = (blockIdx.y * 128 + threadIdx.x) * 8;
+  if (c0 >= C) return;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+
+  const int bid = blockIdx.x;
+  long long out_row;
+  float denom;
+  if (bid < n_temporal) {
+    out_row = bid;
+    if (bid < T) {
+      const uint16_t* src = feats + (long long)bid * frame_stride + c0;
+      int p = 0;
+      for (; p + UNROLL <= P; p += UNROLL) {
+        uint4 u[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) u[k] = ld_nc_v4(src + (long long)(p + k) * patch_stride);
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) acc8<IN_BF16>(u[k], a);
+      }
+      for (; p < P; ++p) acc8<IN_BF16>(ld_nc_v4(src + (long long)p * patch_stride), a);
+      denom = (float)P;
+    } else {
+      denom = 1.f;  // zero padding row
+    }
+  } else {
+    const int p = bid - n_temporal;
+    out_row = bid;
+    const uint16_t* src = feats + (long long)p * patch_stride + c0;
+    int t = 0;
+    for (; t + UNROLL <= T; t += UNROLL) {
+      uint4 u[UNROLL];
+#pragma unroll
+      for (int k = 0; k < UNROLL; ++k) u[k] = ld_nc_v4(src + (long long)(t + k) * frame_stride);
+#pragma unroll
+      for (int k = 0; k < UNROLL; ++k) acc8<IN_BF16>(u[k], a);
+    }
+    for (; t < T; ++t) acc8<IN_BF16>(ld_nc_v4(src + (long long)t * frame_stride), a);
+    denom = (float)T;
+  }
+  uint4 o;
+  o.x = round_pair<IN_BF16, OUT_BF16>(a[0] / denom, a[1] / denom);
+  o.y = round_pair<IN_BF16, OUT_BF16>(a[2] / denom, a[3] / denom);
+  o.z = round_pair<IN_BF16, OUT_BF16>(a[4] / denom, a[5] / denom);
+  o.w = round_pair<IN_BF16, OUT_BF16>(a[6] / denom, a[7] / denom);
+  *reinterpret_cast<uint4*>(out + out_row * C + c0) = o;
+}
+
+}  // namespace
+
+int launch_st_pool(const void* feats, int in_dtype, long long frame_stride, long long patch_stride,
+                   int T, int P, int C, int n_temporal, void* out, int out_dtype,
+                   cudaStream_t stream) {
+  VCL_REQUIRE(T >= 0 && P > 0 && C > 0 && n_temporal >= 0, "st_pool: bad shape T=%d P=%d C=%d", T, P, C);
+  VCL_REQUIRE(T <= n_temporal, "st_pool: T=%d exceeds the %d temporal slots (the reference does not "
+              "guard this; load_video never yields more)", T, n_temporal);
+  VCL_REQUIRE(T > 0, "st_pool: T=0 would divide by zero in the spatial mean");
+  VCL_REQUIRE(C % 8 == 0, "st_pool: C=%d must be a multiple of 8", C);
+  VCL_REQUIRE(frame_stride % 8 == 0 && patch_stride % 8 == 0 && ((uintptr_t)feats % 16) == 0 &&
+                  ((uintptr_t)out % 16) == 0, "st_pool: 16-byte alignment required");
+  VCL_REQUIRE((in_dtype | 1) == 1 && (out_dtype | 1) == 1, "st_pool: dtype codes are 0=fp16 1=bf16");
+  dim3 grid(n_temporal + P, (C / 8 + 127) / 128);
+  const uint16_t* f = reinterpret_cast<const uint16_t*>(feats);
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+#define VCL_POOL(IB, OB) \
+  st_pool_kernel<IB, OB><<<grid, 128, 0, stream>>>(f, frame_stride, patch_stride, T, P, C, n_temporal, o)
+  if (in_dtype == 1 && out_dtype == 1) VCL_POOL(true, true);
+  else if (in_dtype == 1 && out_dtype == 0) VCL_POOL(true, false);
+  else if (in_dtype == 0 && out_dtype == 1) VCL_POOL(false, true);
+  else VCL_POOL(false, false);
+#undef VCL_POOL
+  VCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vcl
