@@ -38,13 +38,16 @@ def _describe(out, ref):
 
 
 def _gemm_ref(a, w, bias, res, act):
+    """Returns (reference, magnitude of the largest bf16 intermediate feeding each output)."""
     y = a.float() @ w.float().t()
     if bias is not None:
         y = y + bias.float()
+    mag = y.abs()
     if act == vn.ACT_SWIGLU:
         g = y[:, 0::2].bfloat16().float()
         u = y[:, 1::2].bfloat16().float()
-        return torch.nn.functional.silu(g).bfloat16().float() * u
+        out = torch.nn.functional.silu(g).bfloat16().float() * u
+        return out, torch.maximum(out.abs(), (g.abs() + 1) * u.abs())
     if act == vn.ACT_QGELU:
         x = y.bfloat16().float()
         y = x * torch.sigmoid((1.702 * x).bfloat16().float()).bfloat16().float()
@@ -52,7 +55,7 @@ def _gemm_ref(a, w, bias, res, act):
         y = torch.nn.functional.gelu(y.bfloat16().float())
     if res is not None:
         y = y.bfloat16().float() + res.float()
-    return y
+    return y, torch.maximum(mag, y.abs())
 
 
 GEMM_CASES = [
@@ -84,14 +87,16 @@ def test_gemm_tcgen05(M, N, K, bn, has_bias, has_res, act):
     bias = torch.randn(N, device=dev).bfloat16() if has_bias else None
     n_out = N // 2 if act == vn.ACT_SWIGLU else N
     res = torch.randn(M, n_out, device=dev).bfloat16() if has_res else None
-    ref = _gemm_ref(a, w, bias, res, act)
+    ref, mag = _gemm_ref(a, w, bias, res, act)
     out = res.clone() if has_res else None  # residual is updated in place on the hot path
     out = vn.op_gemm(a, w, bias, out if has_res else None, act, bn, out=out)
     torch.cuda.synchronize()
     rel = _rel(out, ref)
     # bf16 output: one rounding of an fp32 accumulation -> 2^-9 rms; allow 3e-3 norm-wise
     assert rel < 3e-3, f"rel={rel:.3e} " + _describe(out, ref)
-    ulp = ref.abs().clamp_min(1e-2) * 2 ** -7
+    # element-wise: a couple of bf16 ulps of the largest intermediate (the reference rounds the
+    # nn.Linear output to bf16 before the activation / residual, and so does the kernel)
+    ulp = mag.clamp_min(1e-2) * 2 ** -7
     assert ((out.float() - ref).abs() <= 2.5 * ulp).all(), _describe(out, ref)
 
 

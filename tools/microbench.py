@@ -56,17 +56,19 @@ def pool_case(T, P, C):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    for bn in (256, 128):
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
+    for bn in ((256, 128) if only in ("all", "gemm") else ()):
         gemm_case(25700, 3072, 1024, bn)
         gemm_case(25700, 1024, 1024, bn, res=True)
         gemm_case(25700, 4096, 1024, bn, act=vn.ACT_QGELU)
         gemm_case(25700, 1024, 4096, bn, res=True)
-    gemm_case(8192, 8192, 8192, 256, bias=False)
-    gemm_case(448, 12288, 4096, 0, bias=False)
-    gemm_case(448, 22016, 4096, 0, act=vn.ACT_SWIGLU, bias=False)
-    gemm_case(448, 4096, 11008, 0, bias=False, res=True)
-    gemm_case(7168, 12288, 4096, 256, bias=False)
-    gemm_case(16, 12288, 4096, 0, bias=False)
+    if only in ("all", "gemm"):
+        gemm_case(8192, 8192, 8192, 256, bias=False)
+        gemm_case(448, 12288, 4096, 0, bias=False)
+        gemm_case(448, 22016, 4096, 0, act=vn.ACT_SWIGLU, bias=False)
+        gemm_case(448, 4096, 11008, 0, bias=False, res=True)
+        gemm_case(7168, 12288, 4096, 256, bias=False)
+        gemm_case(16, 12288, 4096, 0, bias=False)
     gemv_case(1, 12288, 4096, True)
     gemv_case(1, 4096, 4096, False)
     gemv_case(1, 22016, 4096, True)

@@ -219,7 +219,7 @@ template <int MODE>
 int launch_mode(int B, const GemvParams& p, cudaStream_t stream) {
   VCL_REQUIRE(B >= 1 && B <= 4, "gemv: batch %d outside 1..4 (larger batches use the tcgen05 GEMM)", B);
   VCL_REQUIRE(p.K % 8 == 0 && p.ldx % 8 == 0, "gemv: K and pitch must be multiples of 8");
-  VCL_REQUIRE((size_t)B * p.K * 4 <= 227 * 1024, "gemv: B*K*4 = %zu exceeds shared memory",
+  VCL_REQUIRE((size_t)B * p.K * 4 <= 226 * 1024, "gemv: B*K*4 = %zu exceeds shared memory",
               (size_t)B * p.K * 4);
   switch (B) {
     case 1: return launch_nb<1, MODE>(p, stream);
@@ -231,7 +231,7 @@ int launch_mode(int B, const GemvParams& p, cudaStream_t stream) {
 
 template <int MODE>
 int init_mode() {
-  const int cap = 227 * 1024;
+  const int cap = 227 * 1024 - 1024;  // static smem (reduction scratch) counts against the limit
   VCL_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<1, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
   VCL_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
   VCL_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
