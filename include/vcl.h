@@ -138,6 +138,16 @@ int vcl_llm_generate(vcl_handle* h, const int64_t* ids, const void* video_feats,
                      const int32_t* vid_start, int B, int S, int n_new, int32_t* out_tokens,
                      void* stream);
 
+/* The decode half of vcl_llm_generate on its own (so a caller can time prefill and decode
+ * separately): first_tok [B] int32 is the token produced by the prefill; runs n_new-1 cached steps
+ * at positions S, S+1, ... and writes [B, n_new] (first_tok included) to out_tokens. */
+int vcl_llm_decode_loop(vcl_handle* h, const int32_t* first_tok, int B, int S, int n_new,
+                        int32_t* out_tokens, void* stream);
+
+/* Number of kernels of this library launched so far in the process (CUDA-graph replays count the
+ * kernel nodes they contain). Evidence for bench.py's "gpu_launches". */
+long long vcl_launch_count(void);
+
 /* ---- single-operator entry points (unit tests / profiling of the individual kernels) ---- */
 /* C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual); act: 0 none, 1 quick_gelu, 2 gelu(erf),
  * 3 swiglu over interleaved rows (C is [M,N/2]). block_n: 0 = auto, or 32/64/128/256. */

@@ -328,6 +328,7 @@ int launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   dim3 grid((a.S + 63) / 64, a.H, a.B);
   kern<<<grid, 128, SMEM, stream>>>(a);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -365,6 +366,7 @@ int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, c
   decode_attn_kernel<<<grid, 256, smem, stream>>>(q, q_ld, kcache, vcache, o, o_ld, H, s_max, kv_len,
                                                   scale);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 

@@ -302,6 +302,7 @@ int launch_layernorm(const bf16* x, long long ldx, bf16* y, long long ldy, const
   if (rows <= 0) return 0;
   rownorm_kernel<false><<<rows, NORM_THREADS, 0, stream>>>(x, ldx, y, ldy, w, b, D, eps);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -312,6 +313,7 @@ int launch_rmsnorm(const bf16* x, long long ldx, bf16* y, long long ldy, const b
   if (rows <= 0) return 0;
   rownorm_kernel<true><<<rows, NORM_THREADS, 0, stream>>>(x, ldx, y, ldy, w, nullptr, D, eps);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -322,6 +324,7 @@ int launch_im2col(const void* pixels, int mode, bf16* out, int n_frames, int ima
   if (n_frames <= 0) return 0;
   im2col_kernel<<<n_frames * (image / patch), 256, 0, stream>>>(pixels, mode, out, image, patch, KP);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -333,6 +336,7 @@ int launch_clip_embed_ln(const bf16* patch_out, const bf16* cls, const bf16* pos
   clip_embed_ln_kernel<<<n_frames * (P + 1), NORM_THREADS, 0, stream>>>(patch_out, cls, pos, ln_w,
                                                                         ln_b, h, P, D, eps);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -343,6 +347,7 @@ int launch_embed_splice(const long long* ids, const bf16* table, const bf16* vid
   if (B * S <= 0) return 0;
   embed_splice_kernel<<<B * S, 128, 0, stream>>>(ids, table, vid, vid_start, h, S, D, n_vid, vocab);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -352,6 +357,7 @@ int launch_embed_tokens(const int* tok, long long tok_stride, const bf16* table,
   if (B <= 0) return 0;
   embed_tokens_kernel<<<B, 128, 0, stream>>>(tok, tok_stride, table, h, D, vocab);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -360,6 +366,7 @@ int launch_rope_table(bf16* cos_t, bf16* sin_t, int max_pos, int head_dim, float
   const int n = max_pos * (head_dim / 2);
   rope_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cos_t, sin_t, max_pos, head_dim, theta);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -373,6 +380,7 @@ int launch_rope_kv_prefill(bf16* qkv, bf16* kcache, bf16* vcache, const bf16* co
   rope_kv_prefill_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(qkv, kcache, vcache, cos_t,
                                                                         sin_t, B, S, H, s_max, pos0);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -381,6 +389,7 @@ int launch_argmax(const float* logits, int* out, long long out_stride, int B, in
   if (B <= 0) return 0;
   argmax_kernel<<<B, 256, 0, stream>>>(logits, out, out_stride, V);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 

@@ -7,8 +7,9 @@
 //   warp 0      TMA producer : cp.async.bulk.tensor 2-D tiles (128B swizzle) -> smem ring
 //   warp 1      MMA issuer   : one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage
 //   warp 2      TMEM allocator (2 accumulator buffers of BLOCK_N fp32 columns)
-//   warps 4-7   epilogue     : tcgen05.ld 32 lanes x 32 columns -> bias / activation / residual
-//                              -> bf16 -> global (64 B contiguous per thread per chunk)
+//   warps 4-11  epilogue     : tcgen05.ld 32 lanes x 32 columns -> bias / activation / residual
+//                              -> bf16 -> global (64 B contiguous per thread per chunk); two warps
+//                              per TMEM lane quarter, software-pipelined over the column chunks
 //
 // Persistent: grid = min(#tiles, #SMs); the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the mainloop of tile i+1.
@@ -58,7 +59,7 @@ __device__ __forceinline__ float act_silu(float g) {
 }
 
 template <int BLOCK_N, int ACT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, bf16* C, long long ldc,
                     const bf16* __restrict__ bias, const bf16* residual, long long ldr, int M,
@@ -94,7 +95,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 256);
     }
     mbar_fence_init();
   }
@@ -161,87 +162,128 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------ epilogue ------------------------------
-    const int ew = warp - 4;                          // == warp % 4: TMEM lane quarter of this warp
+    // ------------------------------ epilogue (8 warps) ------------------------------
+    // warp w reads TMEM lanes 32*(w%4).. (hardware restriction) and owns one half of the tile's
+    // 32-column chunks; the tcgen05.ld and the residual loads of chunk i+1 are issued before the
+    // math of chunk i so their latency hides behind it.
+    const int q4 = warp & 3;
+    const int hf = (warp - 4) >> 2;
+    constexpr int CH = BLOCK_N / 32;
+    constexpr int PER = (CH + 1) / 2;
+    const int c_begin = hf * PER;
+    const int n_mine = (c_begin + PER <= CH) ? PER : (CH > c_begin ? CH - c_begin : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row = m_blk * Cfg::BLOCK_M + q4 * 32 + lane;
+      const bool row_ok = row < M;
+      const int colbase = n_blk * BLOCK_N + c_begin * 32;
+      const bf16* rrow = residual + (long long)row * ldr + colbase;
+      const bool has_res = (residual != nullptr) && row_ok;
+      uint32_t v[2][32];
+      uint4 rr[2][4];
+      if (has_res && n_mine > 0 && colbase < N) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rr[0][q] = *reinterpret_cast<const uint4*>(rrow + q * 8);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m_blk * Cfg::BLOCK_M + ew * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-      const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
-        tmem_ld_32x32(taddr + c * 32, v);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * BLOCK_N + c_begin * 32;
+      __syncwarp();
+      if (n_mine > 0) {
+        tmem_ld_32x32(taddr, v[0]);
         tc_wait_ld();
-        if (c == BLOCK_N / 32 - 1) {
-          // every TMEM read of this accumulator has completed: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
-        }
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (!row_ok || col0 >= N) continue;
-        float f[32];
+      }
+      if (n_mine <= 1) {
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+      }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias != nullptr) {
+      for (int i = 0; i < PER; ++i) {
+        if (i < n_mine) {
+          const int cur = i & 1, nxt = cur ^ 1;
+          const int col0 = colbase + i * 32;
+          if (i + 1 < n_mine) {
+            if (has_res && col0 + 32 < N) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 b = *reinterpret_cast<const uint4*>(bias + col0 + q * 8);
-            f[q * 8 + 0] += bf16lo(b.x); f[q * 8 + 1] += bf16hi(b.x);
-            f[q * 8 + 2] += bf16lo(b.y); f[q * 8 + 3] += bf16hi(b.y);
-            f[q * 8 + 4] += bf16lo(b.z); f[q * 8 + 5] += bf16hi(b.z);
-            f[q * 8 + 6] += bf16lo(b.w); f[q * 8 + 7] += bf16hi(b.w);
+              for (int q = 0; q < 4; ++q)
+                rr[nxt][q] = *reinterpret_cast<const uint4*>(rrow + (i + 1) * 32 + q * 8);
+            }
+            __syncwarp();
+            tmem_ld_32x32(taddr + (i + 1) * 32, v[nxt]);
           }
-        }
-        if constexpr (ACT == ACT_SWIGLU) {
-          // weight rows are interleaved (2j = gate_j, 2j+1 = up_j): 32 columns -> 16 outputs
-          uint32_t o[8];
+          if (row_ok && col0 < N) {
+            float f[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float y0 = act_silu(f[4 * j + 0]) * bf16r(f[4 * j + 1]);
-            const float y1 = act_silu(f[4 * j + 2]) * bf16r(f[4 * j + 3]);
-            o[j] = pack_bf16x2(y0, y1);
-          }
-          bf16* dst = C + (long long)row * ldc + (col0 >> 1);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
-        } else {
-          if constexpr (ACT == ACT_QGELU) {
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[cur][j]);
+            if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = act_quick_gelu(f[j]);
-          } else if constexpr (ACT == ACT_GELU) {
+              for (int q = 0; q < 4; ++q) {
+                const uint4 b = *reinterpret_cast<const uint4*>(bias + col0 + q * 8);
+                f[q * 8 + 0] += bf16lo(b.x); f[q * 8 + 1] += bf16hi(b.x);
+                f[q * 8 + 2] += bf16lo(b.y); f[q * 8 + 3] += bf16hi(b.y);
+                f[q * 8 + 4] += bf16lo(b.z); f[q * 8 + 5] += bf16hi(b.z);
+                f[q * 8 + 6] += bf16lo(b.w); f[q * 8 + 7] += bf16hi(b.w);
+              }
+            }
+            if constexpr (ACT == ACT_SWIGLU) {
+              // weight rows are interleaved (2j = gate_j, 2j+1 = up_j): 32 columns -> 16 outputs
+              uint32_t o[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = act_gelu_erf(f[j]);
-          }
-          if (residual != nullptr) {
-            const bf16* rsrc = residual + (long long)row * ldr + col0;
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t g2 = pack_bf16x2(f[4 * j + 0], f[4 * j + 2]);   // gate pair (bf16)
+                const uint32_t u2 = pack_bf16x2(f[4 * j + 1], f[4 * j + 3]);   // up pair (bf16)
+                const float g0 = bf16lo(g2), g1 = bf16hi(g2);
+                const uint32_t s2 = pack_bf16x2(__fdividef(g0, 1.0f + __expf(-g0)),
+                                                __fdividef(g1, 1.0f + __expf(-g1)));   // silu (bf16)
+                o[j] = bf16x2_mul(s2, u2);
+              }
+              bf16* dst = C + (long long)row * ldc + (col0 >> 1);
+              *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+            } else {
+              uint32_t o[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 r = *reinterpret_cast<const uint4*>(rsrc + q * 8);
-              f[q * 8 + 0] = bf16r(f[q * 8 + 0]) + bf16lo(r.x);
-              f[q * 8 + 1] = bf16r(f[q * 8 + 1]) + bf16hi(r.x);
-              f[q * 8 + 2] = bf16r(f[q * 8 + 2]) + bf16lo(r.y);
-              f[q * 8 + 3] = bf16r(f[q * 8 + 3]) + bf16hi(r.y);
-              f[q * 8 + 4] = bf16r(f[q * 8 + 4]) + bf16lo(r.z);
-              f[q * 8 + 5] = bf16r(f[q * 8 + 5]) + bf16hi(r.z);
-              f[q * 8 + 6] = bf16r(f[q * 8 + 6]) + bf16lo(r.w);
-              f[q * 8 + 7] = bf16r(f[q * 8 + 7]) + bf16hi(r.w);
+              for (int j = 0; j < 16; ++j) {
+                if constexpr (ACT == ACT_QGELU) {
+                  // x*sigmoid(1.702x): the three bf16 tensors of the reference are materialised
+                  const uint32_t x2 = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                  const uint32_t t2 = pack_bf16x2(1.702f * bf16lo(x2), 1.702f * bf16hi(x2));
+                  const uint32_t s2 = pack_bf16x2(__fdividef(1.0f, 1.0f + __expf(-bf16lo(t2))),
+                                                  __fdividef(1.0f, 1.0f + __expf(-bf16hi(t2))));
+                  o[j] = bf16x2_mul(x2, s2);
+                } else if constexpr (ACT == ACT_GELU) {
+                  o[j] = pack_bf16x2(act_gelu_erf(f[2 * j]), act_gelu_erf(f[2 * j + 1]));
+                } else {
+                  o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                }
+              }
+              if (has_res) {
+                // bf16(linear output) + residual, one more bf16 rounding (packed bf16x2 add)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  o[q * 4 + 0] = bf16x2_add(o[q * 4 + 0], rr[cur][q].x);
+                  o[q * 4 + 1] = bf16x2_add(o[q * 4 + 1], rr[cur][q].y);
+                  o[q * 4 + 2] = bf16x2_add(o[q * 4 + 2], rr[cur][q].z);
+                  o[q * 4 + 3] = bf16x2_add(o[q * 4 + 3], rr[cur][q].w);
+                }
+              }
+              bf16* dst = C + (long long)row * ldc + col0;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(dst + q * 8) =
+                    make_uint4(o[q * 4 + 0], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
             }
           }
-          bf16* dst = C + (long long)row * ldc + col0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
-            o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
-            o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
-            o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(dst + q * 8) = o;
+          if (i + 1 < n_mine) {
+            __syncwarp();
+            tc_wait_ld();
+            if (i + 2 >= n_mine) {
+              // every TMEM read of this accumulator has completed: hand it back to the MMA warp
+              tc_fence_before();
+              mbar_arrive(tempty_bar(acc));
+            }
           }
         }
       }
@@ -318,9 +360,10 @@ static int launch_one(const GemmArgs& g, cudaStream_t stream) {
   const int num_tiles = ((g.M + 127) / 128) * ((g.N + BLOCK_N - 1) / BLOCK_N);
   int grid = num_tiles < device_num_sms() ? num_tiles : device_num_sms();
   if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, g.C, g.ldc, g.bias, g.residual, g.ldr, g.M,
+  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, g.C, g.ldc, g.bias, g.residual, g.ldr, g.M,
                                               g.N, g.K);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 

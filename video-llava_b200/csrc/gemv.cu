@@ -212,6 +212,7 @@ int launch_nb(const GemvParams& p, cudaStream_t stream) {
   if (grid > need) grid = need;
   kern<<<grid, GEMV_THREADS, smem, stream>>>(p);
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 

@@ -13,6 +13,8 @@ typedef __nv_bfloat16 bf16;
 enum Act { ACT_NONE = 0, ACT_QGELU = 1, ACT_GELU = 2, ACT_SWIGLU = 3 };
 
 void set_last_error(const char* fmt, ...);
+void count_launches(long long n);
+long long launch_count();
 int device_num_sms();
 
 // ---- gemm_tc.cu : C[M,N] = epi(A[M,K] . W[N,K]^T), tcgen05 + TMA -------------------------------

@@ -10,11 +10,12 @@
 //
 // HBM-bound: 2*T*P*C bytes in, (n_temporal+P)*C*2 out (52.4 MB / 0.73 MB at T=100, P=256).
 // One launch, two CTA roles, no atomics and a fixed summation order (deterministic):
-//   blockIdx <  T        temporal role: CTA walks the P patch rows of one frame
-//   blockIdx >= T        spatial  role: CTA walks the T frames of one patch row
-// Every thread owns 8 consecutive channels (one 128-bit load per row) and keeps UNROLL loads in
-// flight; both roles stream the same tensor concurrently so the second touch of a line is an L2
-// hit rather than a second HBM read.
+//   blockIdx <  n_temporal   temporal role: CTA reduces the P patch rows of one frame
+//   blockIdx >= n_temporal   spatial  role: CTA reduces the T frames of one patch row
+// A CTA is 128 x 8 threads: thread x owns 8 consecutive channels (one 128-bit load per row), the 8
+// y-groups split the rows round-robin with 4 loads in flight each (64 KB in flight per CTA), and a
+// fixed-order shared-memory combine finishes the sum. Both roles stream the same tensor
+// concurrently, so the second touch of a line is an L2 hit rather than a second HBM read.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -48,58 +49,64 @@ __device__ __forceinline__ uint32_t round_pair(float x, float y) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+constexpr int POOL_GROUPS = 8;   // row groups per CTA (threadIdx.y); 128 x 8 = 1024 threads
+
 template <bool IN_BF16, bool OUT_BF16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128 * POOL_GROUPS)
 st_pool_kernel(const uint16_t* __restrict__ feats, long long frame_stride, long long patch_stride,
                int T, int P, int C, int n_temporal, uint16_t* __restrict__ out) {
-  constexpr int UNROLL = 8;
+  constexpr int UNROLL = 4;
+  __shared__ float red[POOL_GROUPS][128 * 8];
+  const int g = threadIdx.y;
   const int c0 = (blockIdx.y * 128 + threadIdx.x) * 8;
-  if (c0 >= C) return;
+  const bool c_ok = c0 < C;
   float a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = 0.f;
 
+  // One output row per CTA; its `n` input rows (stride `step`) are dealt round-robin to the 8
+  // thread groups, each keeping UNROLL 128-bit loads in flight per thread.
   const int bid = blockIdx.x;
-  long long out_row;
-  float denom;
+  const uint16_t* src = feats;
+  long long step = 0;
+  int n = 0;
   if (bid < n_temporal) {
-    out_row = bid;
-    if (bid < T) {
-      const uint16_t* src = feats + (long long)bid * frame_stride + c0;
-      int p = 0;
-      for (; p + UNROLL <= P; p += UNROLL) {
-        uint4 u[UNROLL];
-#pragma unroll
-        for (int k = 0; k < UNROLL; ++k) u[k] = ld_nc_v4(src + (long long)(p + k) * patch_stride);
-#pragma unroll
-        for (int k = 0; k < UNROLL; ++k) acc8<IN_BF16>(u[k], a);
-      }
-      for (; p < P; ++p) acc8<IN_BF16>(ld_nc_v4(src + (long long)p * patch_stride), a);
-      denom = (float)P;
-    } else {
-      denom = 1.f;  // zero padding row
-    }
+    if (bid < T) { src = feats + (long long)bid * frame_stride; step = patch_stride; n = P; }
   } else {
-    const int p = bid - n_temporal;
-    out_row = bid;
-    const uint16_t* src = feats + (long long)p * patch_stride + c0;
-    int t = 0;
-    for (; t + UNROLL <= T; t += UNROLL) {
+    src = feats + (long long)(bid - n_temporal) * patch_stride; step = frame_stride; n = T;
+  }
+  if (c_ok) {
+    src += c0;
+    int r = g;
+    for (; r + (UNROLL - 1) * POOL_GROUPS < n; r += UNROLL * POOL_GROUPS) {
       uint4 u[UNROLL];
 #pragma unroll
-      for (int k = 0; k < UNROLL; ++k) u[k] = ld_nc_v4(src + (long long)(t + k) * frame_stride);
+      for (int k = 0; k < UNROLL; ++k) u[k] = ld_nc_v4(src + (long long)(r + k * POOL_GROUPS) * step);
 #pragma unroll
       for (int k = 0; k < UNROLL; ++k) acc8<IN_BF16>(u[k], a);
     }
-    for (; t < T; ++t) acc8<IN_BF16>(ld_nc_v4(src + (long long)t * frame_stride), a);
-    denom = (float)T;
+    for (; r < n; r += POOL_GROUPS) acc8<IN_BF16>(ld_nc_v4(src + (long long)r * step), a);
   }
-  uint4 o;
-  o.x = round_pair<IN_BF16, OUT_BF16>(a[0] / denom, a[1] / denom);
-  o.y = round_pair<IN_BF16, OUT_BF16>(a[2] / denom, a[3] / denom);
-  o.z = round_pair<IN_BF16, OUT_BF16>(a[4] / denom, a[5] / denom);
-  o.w = round_pair<IN_BF16, OUT_BF16>(a[6] / denom, a[7] / denom);
-  *reinterpret_cast<uint4*>(out + out_row * C + c0) = o;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[g][threadIdx.x * 8 + j] = a[j];
+  __syncthreads();
+  if (g == 0 && c_ok) {
+    // fixed-order combine of the 8 partial sums (deterministic), then the two roundings
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = red[0][threadIdx.x * 8 + j];
+#pragma unroll
+      for (int k = 1; k < POOL_GROUPS; ++k) s += red[k][threadIdx.x * 8 + j];
+      a[j] = s;
+    }
+    const float denom = n > 0 ? (float)n : 1.f;   // n == 0: zero padding row
+    uint4 o;
+    o.x = round_pair<IN_BF16, OUT_BF16>(a[0] / denom, a[1] / denom);
+    o.y = round_pair<IN_BF16, OUT_BF16>(a[2] / denom, a[3] / denom);
+    o.z = round_pair<IN_BF16, OUT_BF16>(a[4] / denom, a[5] / denom);
+    o.w = round_pair<IN_BF16, OUT_BF16>(a[6] / denom, a[7] / denom);
+    *reinterpret_cast<uint4*>(out + (long long)bid * C + c0) = o;
+  }
 }
 
 }  // namespace
@@ -119,13 +126,14 @@ int launch_st_pool(const void* feats, int in_dtype, long long frame_stride, long
   const uint16_t* f = reinterpret_cast<const uint16_t*>(feats);
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
 #define VCL_POOL(IB, OB) \
-  st_pool_kernel<IB, OB><<<grid, 128, 0, stream>>>(f, frame_stride, patch_stride, T, P, C, n_temporal, o)
+  st_pool_kernel<IB, OB><<<grid, dim3(128, POOL_GROUPS), 0, stream>>>(f, frame_stride, patch_stride, T, P, C, n_temporal, o)
   if (in_dtype == 1 && out_dtype == 1) VCL_POOL(true, true);
   else if (in_dtype == 1 && out_dtype == 0) VCL_POOL(true, false);
   else if (in_dtype == 0 && out_dtype == 1) VCL_POOL(false, true);
   else VCL_POOL(false, false);
 #undef VCL_POOL
   VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 

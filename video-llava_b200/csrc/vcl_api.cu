@@ -21,6 +21,11 @@
 namespace vcl {
 
 static thread_local char g_err[1024] = "";
+static long long g_launches = 0;
+
+// Every kernel launcher calls count_launches(1); graph replays add their node count.
+void count_launches(long long n) { g_launches += n; }
+long long launch_count() { return g_launches; }
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;
@@ -44,6 +49,7 @@ struct LlmLayerW {
 struct GraphEntry {
   int B, S, n_new;
   cudaGraphExec_t exec;
+  long long kernels;   // kernel nodes in the graph (for vcl_launch_count)
 };
 
 }  // namespace
@@ -569,27 +575,33 @@ int vcl_llm_decode_step(vcl_handle* h, const int32_t* tok_in, int B, int pos, fl
   return llm_decode_step(h, tok_in, 1, B, pos, logits_out, tok_out, 1, as_stream(stream));
 }
 
-int vcl_llm_generate(vcl_handle* h, const int64_t* ids, const void* video_feats,
-                     const int32_t* vid_start, int B, int S, int n_new, int32_t* out_tokens,
-                     void* stream) {
-  VCL_REQUIRE(h && out_tokens, "vcl_llm_generate: null argument");
+int vcl_llm_decode_loop(vcl_handle* h, const int32_t* first_tok, int B, int S, int n_new,
+                        int32_t* out_tokens, void* stream) {
+  VCL_REQUIRE(h && first_tok && out_tokens, "vcl_llm_decode_loop: null argument");
+  VCL_REQUIRE(h->llm_loaded, "LLM weights are not loaded");
+  VCL_REQUIRE(B > 0 && B <= h->cfg.max_batch, "B=%d outside 1..%d", B, h->cfg.max_batch);
   VCL_REQUIRE(n_new >= 1 && S + n_new <= h->cfg.max_seq + 1, "S + n_new = %d exceeds max_seq %d", S + n_new,
               h->cfg.max_seq);
   cudaStream_t st = as_stream(stream);
   int32_t* tk = h->tokens;  // [B, n_new] row-major scratch
-  VCL_TRY(llm_prefill(h, ids, video_feats, vid_start, B, S, h->cfg.llm_layers, nullptr, nullptr, tk, n_new, st));
+  if (first_tok != tk)
+    VCL_CUDA_OK(cudaMemcpy2DAsync(tk, (size_t)n_new * sizeof(int32_t), first_tok, sizeof(int32_t),
+                                  sizeof(int32_t), B, cudaMemcpyDeviceToDevice, st));
   if (n_new > 1) {
-    cudaGraphExec_t exec = nullptr;
+    GraphEntry* ge = nullptr;
     for (auto& g : h->graphs)
-      if (g.B == B && g.S == S && g.n_new == n_new) exec = g.exec;
+      if (g.B == B && g.S == S && g.n_new == n_new) ge = &g;
     const bool can_capture = (st != nullptr) && (st != cudaStreamLegacy);
-    if (exec == nullptr && can_capture) {
+    if (ge == nullptr && can_capture) {
+      const long long before = launch_count();
       VCL_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       int rc = 0;
       for (int i = 1; i < n_new && rc == 0; ++i)
         rc = llm_decode_step(h, tk + (i - 1), n_new, B, S + i - 1, nullptr, tk + i, n_new, st);
       cudaGraph_t graph = nullptr;
       cudaError_t e = cudaStreamEndCapture(st, &graph);
+      const long long nodes = launch_count() - before;
+      count_launches(-nodes);  // captured, not executed
       if (rc != 0) {
         if (graph) cudaGraphDestroy(graph);
         return rc;
@@ -598,16 +610,19 @@ int vcl_llm_generate(vcl_handle* h, const int64_t* ids, const void* video_feats,
         set_last_error("decode graph capture failed: %s", cudaGetErrorString(e));
         return -2;
       }
+      cudaGraphExec_t exec = nullptr;
       e = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       if (e != cudaSuccess) {
         set_last_error("decode graph instantiate failed: %s", cudaGetErrorString(e));
         return -2;
       }
-      h->graphs.push_back({B, S, n_new, exec});
+      h->graphs.push_back({B, S, n_new, exec, nodes});
+      ge = &h->graphs.back();
     }
-    if (exec != nullptr) {
-      VCL_CUDA_OK(cudaGraphLaunch(exec, st));
+    if (ge != nullptr) {
+      VCL_CUDA_OK(cudaGraphLaunch(ge->exec, st));
+      count_launches(ge->kernels);
     } else {
       for (int i = 1; i < n_new; ++i)
         VCL_TRY(llm_decode_step(h, tk + (i - 1), n_new, B, S + i - 1, nullptr, tk + i, n_new, st));
@@ -616,6 +631,20 @@ int vcl_llm_generate(vcl_handle* h, const int64_t* ids, const void* video_feats,
   VCL_CUDA_OK(cudaMemcpyAsync(out_tokens, tk, (size_t)B * n_new * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
+
+int vcl_llm_generate(vcl_handle* h, const int64_t* ids, const void* video_feats,
+                     const int32_t* vid_start, int B, int S, int n_new, int32_t* out_tokens,
+                     void* stream) {
+  VCL_REQUIRE(h && out_tokens, "vcl_llm_generate: null argument");
+  VCL_REQUIRE(n_new >= 1 && S + n_new <= h->cfg.max_seq + 1, "S + n_new = %d exceeds max_seq %d", S + n_new,
+              h->cfg.max_seq);
+  cudaStream_t st = as_stream(stream);
+  VCL_TRY(llm_prefill(h, ids, video_feats, vid_start, B, S, h->cfg.llm_layers, nullptr, nullptr, h->tokens,
+                      n_new, st));
+  return vcl_llm_decode_loop(h, h->tokens, B, S, n_new, out_tokens, stream);
+}
+
+long long vcl_launch_count(void) { return launch_count(); }
 
 // ---- single-operator entry points ----
 int vcl_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,

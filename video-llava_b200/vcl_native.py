@@ -58,6 +58,8 @@ _SIGNATURES = {
     "vcl_llm_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vcl_llm_generate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_void_p]),
+    "vcl_llm_decode_loop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vcl_launch_count": (ctypes.c_longlong, []),
     "vcl_op_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                             c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vcl_op_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
@@ -186,6 +188,10 @@ def _tensor_array(state: dict, keep: list):
     return arr
 
 
+def launch_count() -> int:
+    return int(lib().vcl_launch_count())
+
+
 class Engine:
     """Owns one vcl_handle (one per process / GPU)."""
 
@@ -234,25 +240,30 @@ class Engine:
         check(lib().vcl_clip_encode(self._h, ptr(pixels), fmt, n, nl, ptr(out), cur_stream()))
         return out
 
-    def clip_features(self, pixels: torch.Tensor, out_dtype=torch.float16) -> torch.Tensor:
+    def clip_features(self, pixels: torch.Tensor, out_dtype=torch.float16, out=None) -> torch.Tensor:
         fmt = PIXELS_U8_NHWC if pixels.dtype == torch.uint8 else PIXELS_BF16_NCHW
         if fmt == PIXELS_BF16_NCHW and pixels.dtype != torch.bfloat16:
             pixels = pixels.to(torch.bfloat16)
         pixels = pixels.contiguous()
-        out = torch.empty(self.NV, self.cfg.clip_hidden, dtype=out_dtype, device=pixels.device)
+        if out is None:
+            out = torch.empty(self.NV, self.cfg.clip_hidden, dtype=out_dtype, device=pixels.device)
+        else:
+            out_dtype = out.dtype
+            assert out.shape == (self.NV, self.cfg.clip_hidden)
         check(lib().vcl_clip_features(self._h, ptr(pixels), fmt, pixels.shape[0], ptr(out),
                                       _dtype_code(out_dtype), cur_stream()))
         return out
 
     # ---- language model ----
     def prefill(self, ids, video_feats, vid_start, n_layers=None, want_hidden=False, want_logits=False,
-                want_token=True):
+                want_token=True, tok_out=None):
         B, S = ids.shape
         nl = self.cfg.llm_layers if n_layers is None else n_layers
         dev = ids.device
         hidden = torch.empty(B, S, self.cfg.llm_hidden, dtype=torch.bfloat16, device=dev) if want_hidden else None
         logits = torch.empty(B, self.cfg.vocab, dtype=torch.float32, device=dev) if want_logits else None
-        tok = torch.empty(B, dtype=torch.int32, device=dev) if want_token else None
+        tok = tok_out if tok_out is not None else (
+            torch.empty(B, dtype=torch.int32, device=dev) if want_token else None)
         vf = None
         if video_feats is not None:
             vf = video_feats.to(torch.bfloat16).contiguous()
@@ -268,6 +279,13 @@ class Engine:
         check(lib().vcl_llm_decode_step(self._h, ptr(tok_in.contiguous()), B, pos, ptr(logits), ptr(tok),
                                         cur_stream()))
         return logits, tok
+
+    def decode_loop(self, first_tok, S, n_new, out=None):
+        B = first_tok.shape[0]
+        if out is None:
+            out = torch.empty(B, n_new, dtype=torch.int32, device=first_tok.device)
+        check(lib().vcl_llm_decode_loop(self._h, ptr(first_tok.contiguous()), B, S, n_new, ptr(out), cur_stream()))
+        return out
 
     def generate(self, ids, video_feats, vid_start, n_new):
         B, S = ids.shape
