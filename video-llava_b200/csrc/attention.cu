@@ -247,26 +247,37 @@ decode_attn_kernel(const bf16* __restrict__ q, long long q_ld, const bf16* __res
   const long long coff = ((long long)b * H + h) * s_max * 128;
   const bf16* kc = kcache + coff;
   const bf16* vc = vcache + coff;
+  // programmatic dependent launch: let the next kernel (o_proj GEMV) start prefetching its weights,
+  // then wait for the producer of q / the cache (the fused QKV GEMV) to complete
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // phase 1: scores. 16 lanes per key (8 dims each), 2 keys per warp iteration.
+  // phase 1: scores. 16 lanes per key (8 dims each): 16 keys per pass of the CTA, U passes in flight.
   {
-    const int half = lane >> 4, dl = lane & 15;
+    constexpr int U = 8;
+    const int kq = threadIdx.x >> 4, dl = threadIdx.x & 15;
     const uint4 qu = *reinterpret_cast<const uint4*>(q + (long long)b * q_ld + h * 128 + dl * 8);
     float qf[8] = {bf16lo(qu.x), bf16hi(qu.x), bf16lo(qu.y), bf16hi(qu.y),
                    bf16lo(qu.z), bf16hi(qu.z), bf16lo(qu.w), bf16hi(qu.w)};
-    for (int j0 = warp * 2; j0 < kv_len; j0 += 16) {
-      const int j = j0 + half;
-      float d = 0.f;
-      if (j < kv_len) {
-        const uint4 ku = ld_nc_v4(kc + (long long)j * 128 + dl * 8);
-        d = qf[0] * bf16lo(ku.x) + qf[1] * bf16hi(ku.x) + qf[2] * bf16lo(ku.y) + qf[3] * bf16hi(ku.y) +
-            qf[4] * bf16lo(ku.z) + qf[5] * bf16hi(ku.z) + qf[6] * bf16lo(ku.w) + qf[7] * bf16hi(ku.w);
+    for (int j0 = kq; j0 < kv_len; j0 += 16 * U) {
+      uint4 ku[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + 16 * u;
+        ku[u] = (j < kv_len) ? ld_nc_v4(kc + (long long)j * 128 + dl * 8) : make_uint4(0, 0, 0, 0);
       }
-      d += __shfl_xor_sync(0xffffffffu, d, 8);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      if (dl == 0 && j < kv_len) sc[j] = bf16r(bf16r(d) * scale);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + 16 * u;
+        float d = qf[0] * bf16lo(ku[u].x) + qf[1] * bf16hi(ku[u].x) + qf[2] * bf16lo(ku[u].y) +
+                  qf[3] * bf16hi(ku[u].y) + qf[4] * bf16lo(ku[u].z) + qf[5] * bf16hi(ku[u].z) +
+                  qf[6] * bf16lo(ku[u].w) + qf[7] * bf16hi(ku[u].w);
+        d += __shfl_xor_sync(0xffffffffu, d, 8);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        if (dl == 0 && j < kv_len) sc[j] = bf16r(bf16r(d) * scale);
+      }
     }
   }
   __syncthreads();
@@ -297,17 +308,27 @@ decode_attn_kernel(const bf16* __restrict__ q, long long q_ld, const bf16* __res
   __syncthreads();
   for (int j = threadIdx.x; j < kv_len; j += 256) sc[j] = bf16r(sc[j] * inv);
   __syncthreads();
-  // phase 3: out = P V. thread = (key group g of 16, 8-dim chunk dc of 16)
+  // phase 3: out = P V. thread = (key group g of 16, 8-dim chunk dc of 16), U loads in flight
   {
+    constexpr int U = 8;
     const int g = threadIdx.x >> 4, dc = threadIdx.x & 15;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int j = g; j < kv_len; j += 16) {
-      const float p = sc[j];
-      const uint4 vu = ld_nc_v4(vc + (long long)j * 128 + dc * 8);
-      acc[0] += p * bf16lo(vu.x); acc[1] += p * bf16hi(vu.x);
-      acc[2] += p * bf16lo(vu.y); acc[3] += p * bf16hi(vu.y);
-      acc[4] += p * bf16lo(vu.z); acc[5] += p * bf16hi(vu.z);
-      acc[6] += p * bf16lo(vu.w); acc[7] += p * bf16hi(vu.w);
+    for (int j0 = g; j0 < kv_len; j0 += 16 * U) {
+      uint4 vu[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + 16 * u;
+        vu[u] = (j < kv_len) ? ld_nc_v4(vc + (long long)j * 128 + dc * 8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + 16 * u;
+        const float p = (j < kv_len) ? sc[j] : 0.f;
+        acc[0] += p * bf16lo(vu[u].x); acc[1] += p * bf16hi(vu[u].x);
+        acc[2] += p * bf16lo(vu[u].y); acc[3] += p * bf16hi(vu[u].y);
+        acc[4] += p * bf16lo(vu[u].z); acc[5] += p * bf16hi(vu[u].z);
+        acc[6] += p * bf16lo(vu[u].w); acc[7] += p * bf16hi(vu[u].w);
+      }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) red[g * 128 + dc * 8 + e] = acc[e];
@@ -362,10 +383,18 @@ int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, c
   VCL_REQUIRE(kv_len > 0 && kv_len <= s_max, "decode attention: kv_len %d out of range", kv_len);
   const size_t smem = (size_t)(kv_len + 16 * 128 + 16) * sizeof(float);
   VCL_REQUIRE(smem <= 48 * 1024, "decode attention: kv_len %d too long for the smem budget", kv_len);
-  dim3 grid(H, B);
-  decode_attn_kernel<<<grid, 256, smem, stream>>>(q, q_ld, kcache, vcache, o, o_ld, H, s_max, kv_len,
-                                                  scale);
-  VCL_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(H, B);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_attn_kernel, q, q_ld, kcache, vcache, o, o_ld, H, s_max,
+                                 kv_len, scale));
   count_launches(1);
   return 0;
 }

@@ -107,6 +107,77 @@ rownorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, 
   norm_store<RMS>(v, nch, D, y + row * ldy, w, b, eps, red);
 }
 
+// Warp-per-row normalisation for the widths on the hot path (D = 256*CPL): every lane owns CPL
+// 16-byte chunks of a row, a warp normalises ROWS rows at once (ROWS*CPL loads in flight per lane),
+// statistics need only shuffles, and a CTA of 8 warps covers 8*ROWS rows. ~HBM speed.
+template <bool RMS, int CPL, int ROWS>
+__global__ void __launch_bounds__(256)
+rownorm_warp_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                    const bf16* __restrict__ w, const bf16* __restrict__ b, int rows, float eps) {
+  constexpr int D = CPL * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
+  uint4 u[ROWS][CPL];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const long long row = row0 + r < rows ? row0 + r : rows - 1;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) u[r][i] = ld_nc_v4(x + row * ldx + (i * 32 + lane) * 8);
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (row0 + r >= rows) break;
+    float v[CPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      unpack8(u[r][i], v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += RMS ? v[i][j] * v[i][j] : v[i][j];
+    }
+    s = warp_sum(s);
+    float mean = 0.f, rstd;
+    if (RMS) {
+      rstd = rsqrtf(s / (float)D + eps);
+    } else {
+      mean = s / (float)D;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+      q = warp_sum(q);
+      rstd = rsqrtf(q / (float)D + eps);
+    }
+    bf16* yr = y + (row0 + r) * ldy;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int c = i * 32 + lane;
+      float wv[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(w + c * 8), wv);
+      if (RMS) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = wv[j] * bf16r(v[i][j] * rstd);
+      } else {
+        float bv[8];
+        unpack8(*reinterpret_cast<const uint4*>(b + c * 8), bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * wv[j] + bv[j];
+      }
+      *reinterpret_cast<uint4*>(yr + c * 8) = pack8(o);
+    }
+  }
+}
+
+template <bool RMS, int CPL, int ROWS>
+void launch_rownorm_warp(const bf16* x, long long ldx, bf16* y, long long ldy, const bf16* w,
+                         const bf16* b, int rows, float eps, cudaStream_t stream) {
+  const int per_cta = 8 * ROWS;
+  rownorm_warp_kernel<RMS, CPL, ROWS><<<(rows + per_cta - 1) / per_cta, 256, 0, stream>>>(x, ldx, y, ldy, w, b,
+                                                                                            rows, eps);
+}
+
 __global__ void __launch_bounds__(NORM_THREADS)
 clip_embed_ln_kernel(const bf16* __restrict__ patch_out, const bf16* __restrict__ cls,
                      const bf16* __restrict__ pos, const bf16* __restrict__ ln_w,
@@ -266,16 +337,26 @@ rope_kv_prefill_kernel(bf16* qkv, bf16* __restrict__ kcache, bf16* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 argmax_kernel(const float* __restrict__ logits, int* __restrict__ out, long long out_stride, int V) {
-  __shared__ float sv[8];
-  __shared__ int si[8];
+  __shared__ float sv[32];
+  __shared__ int si[32];
   const float* l = logits + (long long)blockIdx.x * V;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float x = l[i];
-    if (x > best || (x == best && i < bi)) { best = x; bi = i; }
+  constexpr int U = 8;
+  for (int i0 = threadIdx.x; i0 < V; i0 += 1024 * U) {
+    float x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 1024;
+      x[u] = (i < V) ? l[i] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 1024;      // increasing index: ties keep the lowest
+      if (x[u] > best) { best = x[u]; bi = i; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -286,10 +367,15 @@ argmax_kernel(const float* __restrict__ logits, int* __restrict__ out, long long
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { sv[warp] = best; si[warp] = bi; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w)
-      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
-    out[(long long)blockIdx.x * out_stride] = bi;
+  if (warp == 0) {
+    best = sv[lane]; bi = si[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) out[(long long)blockIdx.x * out_stride] = bi;
   }
 }
 
@@ -300,7 +386,8 @@ int launch_layernorm(const bf16* x, long long ldx, bf16* y, long long ldy, const
   VCL_REQUIRE(D % 8 == 0 && D <= NORM_MAXC * 8 * NORM_THREADS, "layernorm: unsupported D=%d", D);
   VCL_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "layernorm: pitches must be x8");
   if (rows <= 0) return 0;
-  rownorm_kernel<false><<<rows, NORM_THREADS, 0, stream>>>(x, ldx, y, ldy, w, b, D, eps);
+  if (D == 1024) launch_rownorm_warp<false, 4, 2>(x, ldx, y, ldy, w, b, rows, eps, stream);
+  else rownorm_kernel<false><<<rows, NORM_THREADS, 0, stream>>>(x, ldx, y, ldy, w, b, D, eps);
   VCL_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -311,7 +398,9 @@ int launch_rmsnorm(const bf16* x, long long ldx, bf16* y, long long ldy, const b
   VCL_REQUIRE(D % 8 == 0 && D <= NORM_MAXC * 8 * NORM_THREADS, "rmsnorm: unsupported D=%d", D);
   VCL_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "rmsnorm: pitches must be x8");
   if (rows <= 0) return 0;
-  rownorm_kernel<true><<<rows, NORM_THREADS, 0, stream>>>(x, ldx, y, ldy, w, nullptr, D, eps);
+  if (D == 4096) launch_rownorm_warp<true, 16, 1>(x, ldx, y, ldy, w, nullptr, rows, eps, stream);
+  else if (D == 5120) launch_rownorm_warp<true, 20, 1>(x, ldx, y, ldy, w, nullptr, rows, eps, stream);
+  else rownorm_kernel<true><<<rows, NORM_THREADS, 0, stream>>>(x, ldx, y, ldy, w, nullptr, D, eps);
   VCL_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -387,7 +476,7 @@ int launch_rope_kv_prefill(bf16* qkv, bf16* kcache, bf16* vcache, const bf16* co
 int launch_argmax(const float* logits, int* out, long long out_stride, int B, int V,
                   cudaStream_t stream) {
   if (B <= 0) return 0;
-  argmax_kernel<<<B, 256, 0, stream>>>(logits, out, out_stride, V);
+  argmax_kernel<<<B, 1024, 0, stream>>>(logits, out, out_stride, V);
   VCL_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return 0;
