@@ -160,6 +160,9 @@ int vcl_op_rmsnorm(const void* x, void* y, const void* w, int rows, int D, float
 /* q,k,v,o: [B,S,H,hd] contiguous bf16 */
 int vcl_op_attention(const void* q, const void* k, const void* v, void* o, int B, int S, int H,
                      int head_dim, float scale, int causal, void* stream);
+/* ViT attention on the fused projection output: qkv [n_frames*S, 3*H*64] (q|k|v) -> out
+ * [n_frames*S, H*64]; tcgen05 kernel, 129 <= S <= 257, non-causal, scale 64^-1/2 */
+int vcl_op_attention_vit(const void* qkv, void* out, int n_frames, int S, int H, void* stream);
 /* out[b,n] = x[b,:].W[n,:] (+res) with optional fused RMSNorm of x; B <= 4 */
 int vcl_op_gemv(const void* x, const void* W, void* out, const void* res, const void* norm_w,
                 float eps, int B, int N, int K, void* stream);

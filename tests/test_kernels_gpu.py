@@ -140,6 +140,25 @@ def test_attention(B, S, H, hd, causal):
     assert rel < 6e-3, rel  # P is rounded un-normalised (flash form) vs normalised in eager
 
 
+@pytest.mark.parametrize("n,S,H", [(3, 257, 16), (2, 257, 2), (4, 200, 3), (2, 129, 1), (2, 256, 2), (100, 257, 16)])
+def test_attention_vit_tcgen05(n, S, H):
+    torch.manual_seed(S + H)
+    dev = _dev()
+    C = H * 64
+    qkv = torch.randn(n * S, 3 * C, device=dev).bfloat16()
+    o = vn.op_attention_vit(qkv, n, S, H)
+    q, k, v = [qkv[:, i * C:(i + 1) * C].float().view(n, S, H, 64).permute(0, 2, 1, 3) for i in range(3)]
+    s = ((q @ k.transpose(-1, -2)).bfloat16().float() * 0.125).bfloat16().float()
+    p = torch.softmax(s, -1).bfloat16().float()
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(n * S, C)
+    d = (o.float() - ref).abs()
+    rel = _rel(o, ref)
+    per_row = (o.float() - ref).norm(dim=1) / ref.norm(dim=1)
+    worst = per_row.argmax().item()
+    assert rel < 6e-3, f"rel={rel:.3e} worst row {worst} (token {worst % S}) err {per_row[worst].item():.3e} maxabs {d.max().item():.3e}"
+    assert per_row.max().item() < 3e-2, f"worst row {worst} (token {worst % S}) err {per_row[worst].item():.3e}"
+
+
 @pytest.mark.parametrize("B,N,K,norm,res", [(1, 4096, 4096, False, True), (1, 12288, 4096, True, False),
                                             (4, 4096, 11008, False, True), (3, 1000, 5120, True, True),
                                             (2, 32003, 4096, True, False)])

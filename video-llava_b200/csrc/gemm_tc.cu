@@ -320,8 +320,8 @@ static int resolve_encode() {
 }
 
 // 2-D bf16 tensor [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long long cols,
-                     long long ld, int box_rows) {
+int make_tmap_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
+                 int box_rows) {
   if (resolve_encode() != 0) return -2;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
@@ -355,8 +355,8 @@ static int launch_one(const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   auto kern = gemm_bf16_tn_kernel<BLOCK_N, ACT>;
   CUtensorMap ta, tb;
-  if (make_tmap(&ta, g.A, g.M, g.K, g.lda, Cfg::BLOCK_M) != 0) return -2;
-  if (make_tmap(&tb, g.W, g.N, g.K, g.ldw, BLOCK_N) != 0) return -2;
+  if (make_tmap_2d(&ta, g.A, g.M, g.K, g.lda, Cfg::BLOCK_M) != 0) return -2;
+  if (make_tmap_2d(&tb, g.W, g.N, g.K, g.ldw, BLOCK_N) != 0) return -2;
   const int num_tiles = ((g.M + 127) / 128) * ((g.N + BLOCK_N - 1) / BLOCK_N);
   int grid = num_tiles < device_num_sms() ? num_tiles : device_num_sms();
   if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;

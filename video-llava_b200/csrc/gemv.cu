@@ -85,7 +85,8 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float s) {
 
 template <int NB, int J, int MODE>
 __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvParams p) {
-  constexpr int G = (J == 1) ? 8 : 4;            // rows per group: G*J loads in flight per lane
+  // rows per group; two groups are kept in flight (software pipeline): 2*G*J 128-bit loads per lane
+  constexpr int G = (J == 1) ? 8 : (J == 2 ? 4 : 2);
   extern __shared__ __align__(16) float part[];  // [GEMV_WARPS][rows_per_cta][NB]
   __shared__ float red[NB][GEMV_WARPS];
   const int K = p.K;
@@ -110,8 +111,9 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvParams 
   };
 
   // weights do not depend on the previous kernel: start streaming them before the dependency wait
-  uint4 wv[G][J];
-  load_group(0, wv);
+  uint4 wa[G][J], wb[G][J];
+  load_group(0, wa);
+  load_group(G, wb);
   pdl_launch_dependents();
   pdl_wait();
 
@@ -163,8 +165,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvParams 
     }
   }
 
-  // ---------------- main loop over this CTA's rows, G at a time ----------------
-  for (int g0 = 0; g0 < n_rows; g0 += G) {
+  // ---------------- main loop over this CTA's rows: two groups of G rows in flight ----------------
+  auto process = [&](int g0, const uint4 (&wv)[G][J]) {
     float acc[G][NB];
 #pragma unroll
     for (int g = 0; g < G; ++g)
@@ -175,7 +177,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvParams 
         for (int j = 0; j < J; ++j) s = dot8(wv[g][j], xv[b][j], s);
         acc[g][b] = s;
       }
-    if (g0 + G < n_rows) load_group(g0 + G, wv);     // next group in flight during the reduction
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
@@ -183,6 +184,14 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvParams 
         const float s = warp_sum(acc[g][b]);
         if (lane == 0 && g0 + g < n_rows) part[(warp * R + g0 + g) * NB + b] = s;
       }
+  };
+  for (int g0 = 0; g0 < n_rows; g0 += 2 * G) {
+    process(g0, wa);
+    if (g0 + 2 * G < n_rows) load_group(g0 + 2 * G, wa);
+    if (g0 + G < n_rows) {
+      process(g0 + G, wb);
+      if (g0 + 3 * G < n_rows) load_group(g0 + 3 * G, wb);
+    }
   }
   __syncthreads();
 

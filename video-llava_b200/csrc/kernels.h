@@ -2,6 +2,7 @@
 // Everything here enqueues on the stream it is given and never synchronises.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -31,6 +32,9 @@ struct GemmArgs {
 };
 int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
 int init_gemm_kernels();
+// 2-D bf16 tensor map [rows, cols] with row pitch ld (elements); box = [box_rows, 64], 128-B swizzle
+int make_tmap_2d(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld,
+                 int box_rows);
 
 // ---- elementwise.cu ---------------------------------------------------------------------------
 // y = LayerNorm(x) * w + b   (rows x D, fp32 statistics, one bf16 rounding)
@@ -83,6 +87,10 @@ struct AttnArgs {
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int init_attention_kernels();
+// ---- attention_tc.cu : tcgen05 attention for the ViT (hd 64, 129 <= S <= 257, non-causal) ----------
+int launch_attention_vit_tc(const bf16* qkv, bf16* out, int n_frames, int S, int H, int C,
+                            cudaStream_t stream);
+int init_attention_tc_kernels();
 // single-query attention against the cache: q [B, H*hd] -> o [B, H*hd]; kv_len keys per clip
 int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, const bf16* vcache,
                             bf16* o, long long o_ld, int B, int H, int head_dim, int s_max,

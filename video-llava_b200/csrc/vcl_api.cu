@@ -9,6 +9,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -81,6 +82,7 @@ struct vcl_handle {
   bf16 *d_h = nullptr, *d_x = nullptr, *d_q = nullptr, *d_qkv = nullptr, *d_attn = nullptr,
        *d_act = nullptr;
   std::vector<GraphEntry> graphs;
+  bool force_legacy_attention = false;
 
   size_t cache_layer_elems() const {
     return (size_t)cfg.max_batch * cfg.llm_heads * cfg.max_seq * 128;
@@ -186,6 +188,8 @@ int vcl_create(vcl_handle** out, const vcl_config* c) {
   int rc = 0;
   rc |= init_gemm_kernels();
   rc |= init_attention_kernels();
+  rc |= init_attention_tc_kernels();
+  h->force_legacy_attention = getenv("VCL_LEGACY_ATTENTION") != nullptr;
   rc |= init_gemv_kernels();
 
   const size_t C = c->clip_hidden, F = c->clip_inter;
@@ -395,7 +399,11 @@ int clip_forward(vcl_handle* h, const void* pixels, int fmt, int n_frames, int n
     a.v = h->v_qkv + 2 * C; a.v_sb = a.q_sb; a.v_sh = 64; a.v_ss = 3 * C;
     a.o = h->v_attn;        a.o_sb = (long long)S * C; a.o_sh = 64; a.o_ss = C;
     a.B = n_frames; a.H = c.clip_heads; a.S = S; a.head_dim = 64; a.scale = scale; a.causal = 0;
-    VCL_TRY(launch_attention(a, st));
+    if (S >= 129 && S <= 257 && !h->force_legacy_attention) {
+      VCL_TRY(launch_attention_vit_tc(h->v_qkv, h->v_attn, n_frames, S, c.clip_heads, C, st));
+    } else {
+      VCL_TRY(launch_attention(a, st));   // 336-px tower (S = 577): flash-style mma.sync kernel
+    }
     VCL_TRY(gemm(h->v_attn, C, w.wo, C, h->v_h, C, w.bo, h->v_h, C, M, C, C, ACT_NONE, st));
     VCL_TRY(launch_layernorm(h->v_h, C, h->v_x, C, w.ln2_w, w.ln2_b, M, C, c.clip_ln_eps, st));
     VCL_TRY(gemm(h->v_x, C, w.w1, C, h->v_act, F, w.b1, nullptr, 0, M, F, C, ACT_QGELU, st));
@@ -691,6 +699,18 @@ int vcl_op_attention(const void* q, const void* k, const void* v, void* o, int B
   a.o = reinterpret_cast<bf16*>(o); a.o_sb = sb; a.o_sh = sh; a.o_ss = ss;
   a.B = B; a.H = H; a.S = S; a.head_dim = head_dim; a.scale = scale; a.causal = causal;
   return launch_attention(a, as_stream(stream));
+}
+
+int vcl_op_attention_vit(const void* qkv, void* out, int n_frames, int S, int H, void* stream) {
+  if (check_device() != 0) return -2;
+  static bool inited = false;
+  if (!inited) {
+    VCL_TRY(init_gemm_kernels());
+    VCL_TRY(init_attention_tc_kernels());
+    inited = true;
+  }
+  return launch_attention_vit_tc(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), n_frames, S, H,
+                                 H * 64, as_stream(stream));
 }
 
 int vcl_op_gemv(const void* x, const void* W, void* out, const void* res, const void* norm_w,

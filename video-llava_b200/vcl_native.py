@@ -66,6 +66,7 @@ _SIGNATURES = {
     "vcl_op_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "vcl_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                  c_float, c_int, c_void_p]),
+    "vcl_op_attention_vit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vcl_op_gemv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int,
                             c_int, c_void_p]),
 }
@@ -159,6 +160,13 @@ def op_attention(q, k, v, scale, causal):
     o = torch.empty_like(q)
     check(lib().vcl_op_attention(ptr(q), ptr(k), ptr(v), ptr(o), B, S, H, hd, scale, int(causal), cur_stream()))
     return o
+
+
+def op_attention_vit(qkv, n_frames, S, H):
+    """qkv: [n_frames*S, 3*H*64] bf16 -> [n_frames*S, H*64] (tcgen05 ViT attention)."""
+    out = torch.empty(n_frames * S, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    check(lib().vcl_op_attention_vit(ptr(qkv), ptr(out), n_frames, S, H, cur_stream()))
+    return out
 
 
 def op_gemv(x, w, res=None, norm_w=None, eps=0.0):
