@@ -77,3 +77,14 @@ if __name__ == "__main__":
     gemv_case(1, 32003, 4096, True)
     pool_case(100, 256, 1024)
     pool_case(100, 576, 1024)
+
+
+def attn_case(n, S, H):
+    qkv = torch.randn(n * S, 3 * H * 64, device=dev).bfloat16()
+    ms = timeit(lambda: vn.op_attention_vit(qkv, n, S, H))
+    fl = n * H * 4.0 * S * S * 64
+    print(f"attn_vit_tc n={n} S={S} H={H}: {ms*1e3:.1f} us {fl/ms/1e9:.0f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__" and (len(sys.argv) < 2 or sys.argv[1] in ("all", "attn")):
+    attn_case(100, 257, 16)

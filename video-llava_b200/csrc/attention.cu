@@ -12,7 +12,7 @@
 //     Round 1 uses the legacy tensor path here (attention is 4 % of the ViT flops and <1 % of the
 //     prefill flops); the tcgen05 version is the next step for this file.
 //
-// (2) decode_attn_kernel: one query row per (clip, head) against the KV cache; HBM/L2-bound.
+// (2) the single-query decode attention lives in decode_attention.cu (cluster of 4 CTAs per head).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -232,116 +232,6 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// decode: q [B, H*128] (already rotated), cache [B, H, s_max, 128]
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-decode_attn_kernel(const bf16* __restrict__ q, long long q_ld, const bf16* __restrict__ kcache,
-                   const bf16* __restrict__ vcache, bf16* __restrict__ o, long long o_ld, int H,
-                   int s_max, int kv_len, float scale) {
-  extern __shared__ float sm[];
-  float* sc = sm;                    // [kv_len] scores -> probabilities
-  float* red = sm + kv_len;          // [16][128] partial outputs (+ 16 scratch)
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long coff = ((long long)b * H + h) * s_max * 128;
-  const bf16* kc = kcache + coff;
-  const bf16* vc = vcache + coff;
-  // programmatic dependent launch: let the next kernel (o_proj GEMV) start prefetching its weights,
-  // then wait for the producer of q / the cache (the fused QKV GEMV) to complete
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  // phase 1: scores. 16 lanes per key (8 dims each): 16 keys per pass of the CTA, U passes in flight.
-  {
-    constexpr int U = 8;
-    const int kq = threadIdx.x >> 4, dl = threadIdx.x & 15;
-    const uint4 qu = *reinterpret_cast<const uint4*>(q + (long long)b * q_ld + h * 128 + dl * 8);
-    float qf[8] = {bf16lo(qu.x), bf16hi(qu.x), bf16lo(qu.y), bf16hi(qu.y),
-                   bf16lo(qu.z), bf16hi(qu.z), bf16lo(qu.w), bf16hi(qu.w)};
-    for (int j0 = kq; j0 < kv_len; j0 += 16 * U) {
-      uint4 ku[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + 16 * u;
-        ku[u] = (j < kv_len) ? ld_nc_v4(kc + (long long)j * 128 + dl * 8) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + 16 * u;
-        float d = qf[0] * bf16lo(ku[u].x) + qf[1] * bf16hi(ku[u].x) + qf[2] * bf16lo(ku[u].y) +
-                  qf[3] * bf16hi(ku[u].y) + qf[4] * bf16lo(ku[u].z) + qf[5] * bf16hi(ku[u].z) +
-                  qf[6] * bf16lo(ku[u].w) + qf[7] * bf16hi(ku[u].w);
-        d += __shfl_xor_sync(0xffffffffu, d, 8);
-        d += __shfl_xor_sync(0xffffffffu, d, 4);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        if (dl == 0 && j < kv_len) sc[j] = bf16r(bf16r(d) * scale);
-      }
-    }
-  }
-  __syncthreads();
-  // phase 2: fp32 softmax, probabilities rounded to bf16 (eager semantics)
-  float mx = -INFINITY;
-  for (int j = threadIdx.x; j < kv_len; j += 256) mx = fmaxf(mx, sc[j]);
-  mx = warp_max(mx);
-  float* scratch = red + 16 * 128;
-  if (lane == 0) scratch[warp] = mx;
-  __syncthreads();
-  mx = scratch[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, scratch[w]);
-  __syncthreads();
-  float sum = 0.f;
-  for (int j = threadIdx.x; j < kv_len; j += 256) {
-    const float e = __expf(sc[j] - mx);
-    sc[j] = e;
-    sum += e;
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) scratch[warp] = sum;
-  __syncthreads();
-  sum = 0.f;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) sum += scratch[w];
-  const float inv = 1.0f / sum;
-  __syncthreads();
-  for (int j = threadIdx.x; j < kv_len; j += 256) sc[j] = bf16r(sc[j] * inv);
-  __syncthreads();
-  // phase 3: out = P V. thread = (key group g of 16, 8-dim chunk dc of 16), U loads in flight
-  {
-    constexpr int U = 8;
-    const int g = threadIdx.x >> 4, dc = threadIdx.x & 15;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int j0 = g; j0 < kv_len; j0 += 16 * U) {
-      uint4 vu[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + 16 * u;
-        vu[u] = (j < kv_len) ? ld_nc_v4(vc + (long long)j * 128 + dc * 8) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + 16 * u;
-        const float p = (j < kv_len) ? sc[j] : 0.f;
-        acc[0] += p * bf16lo(vu[u].x); acc[1] += p * bf16hi(vu[u].x);
-        acc[2] += p * bf16lo(vu[u].y); acc[3] += p * bf16hi(vu[u].y);
-        acc[4] += p * bf16lo(vu[u].z); acc[5] += p * bf16hi(vu[u].z);
-        acc[6] += p * bf16lo(vu[u].w); acc[7] += p * bf16hi(vu[u].w);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) red[g * 128 + dc * 8 + e] = acc[e];
-  }
-  __syncthreads();
-  if (threadIdx.x < 128) {
-    float v = 0.f;
-#pragma unroll
-    for (int g = 0; g < 16; ++g) v += red[g * 128 + threadIdx.x];
-    o[(long long)b * o_ld + h * 128 + threadIdx.x] = __float2bfloat16_rn(v);
-  }
-}
-
 template <int HD, bool CAUSAL>
 int launch_attn_t(const AttnArgs& a, cudaStream_t stream) {
   constexpr int SMEM = 5 * 64 * HD * 2;
@@ -374,29 +264,6 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     return a.causal ? launch_attn_t<64, true>(a, stream) : launch_attn_t<64, false>(a, stream);
   }
   return a.causal ? launch_attn_t<128, true>(a, stream) : launch_attn_t<128, false>(a, stream);
-}
-
-int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, const bf16* vcache,
-                            bf16* o, long long o_ld, int B, int H, int head_dim, int s_max,
-                            int kv_len, float scale, cudaStream_t stream) {
-  VCL_REQUIRE(head_dim == 128, "decode attention: head_dim must be 128");
-  VCL_REQUIRE(kv_len > 0 && kv_len <= s_max, "decode attention: kv_len %d out of range", kv_len);
-  const size_t smem = (size_t)(kv_len + 16 * 128 + 16) * sizeof(float);
-  VCL_REQUIRE(smem <= 48 * 1024, "decode attention: kv_len %d too long for the smem budget", kv_len);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(H, B);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_attn_kernel, q, q_ld, kcache, vcache, o, o_ld, H, s_max,
-                                 kv_len, scale));
-  count_launches(1);
-  return 0;
 }
 
 }  // namespace vcl

@@ -3,20 +3,24 @@
 // One CTA per (frame, head). The S x S problem is tiny (257 x 257 for ViT-L/14 @224), so the whole
 // K and V of the head live in shared memory and the scores of 128 queries x 256 keys live in TMEM:
 //
-//   warp 8 (1 thread)  TMA: Q, K, V tiles [256 rows x 64] of this (frame, head) straight out of the
+//   warp 16 (1 thread) TMA: Q, K, V tiles [256 rows x 64] of this (frame, head) straight out of the
 //                      fused qkv activation (128-B swizzle); then issues all tcgen05.mma:
 //                        S_t = Q_t . K^T      M128 x N256 x K64   -> TMEM columns [256t, 256t+256)
 //                        O_t = P_t . V        M128 x N64  x K256  -> TMEM columns [256t, 256t+64)
 //                      (V is used as an MN-major B operand, so no transpose is ever materialised)
-//   warps 0-7          softmax: thread (row, half) reads its 128 score columns from TMEM twice
-//                      (max, then exp2 + sum), writes P as bf16 into a K-major swizzled smem tile
-//                      that the second MMA consumes, then normalises and stores O
-//   warp 9             TMEM allocator; computes query row 256 (the 257th token) on CUDA cores
+//   warps 0-15         softmax: thread (row, column quarter) reads its 64 score columns from TMEM
+//                      twice (max, then exp2 + sum), writes P as bf16 into a K-major swizzled smem
+//                      tile that the second MMA consumes, then normalises and stores 16 O columns
+//   warp 17            TMEM allocator; softmax + PV of query row 256 (the 257th token)
 //
-// S = 257 = 2*128 + 1: the 257th KEY is folded in analytically by the softmax threads (one extra
-// 64-long dot product per query row, added to the max / sum / output), and the 257th QUERY row is
-// a 33k-MAC problem done by one warp -- this keeps the tensor-core problem at exactly two M128 x
-// N256 tiles and TMEM at exactly 512 columns.
+// S = 257 = 2*128 + 1: the 257th KEY is folded in analytically (one extra 64-long dot product per
+// query row, added to the max / sum / output), and the 257th QUERY row is a 33k-MAC problem whose
+// scores are computed by the softmax threads (one dot product each) and finished by warp 17 --
+// this keeps the tensor-core problem at exactly two M128 x N256 tiles and TMEM at 512 columns.
+//
+// The kernel is bound by CUDA-core work (exp2 on the MUFU pipe and the instructions around it),
+// not by the MMAs (6.6 % tensor-pipe active in the first version), so the softmax is spread over 16
+// warps and its inner loop is kept to ~5 instructions per score.
 //
 // Arithmetic follows transformers/models/clip/modeling_clip.py:261-279 (eager): the score tensor
 // is rounded to bf16 before the (exact, 2^-3) scaling, softmax statistics are fp32, P is rounded to
@@ -32,24 +36,27 @@ namespace vcl {
 
 namespace {
 
-constexpr int ATC_THREADS = 320;
+constexpr int SM_WARPS = 16;                     // softmax warps
+constexpr int SM_THREADS = SM_WARPS * 32;        // 512
+constexpr int ATC_THREADS = SM_THREADS + 64;     // + MMA/TMA warp + tail warp
 constexpr int TILE_BYTES = 256 * 128;            // 256 rows x 64 bf16
 constexpr int P_BYTES = 128 * 256 * 2;           // one P tile: 4 K-blocks of [128 x 64]
 // smem map (1024-aligned): [Q | K] 64 KB (re-used by P1), V 32 KB, P0 64 KB, small arrays
 constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = 2 * TILE_BYTES, OFF_P0 = 3 * TILE_BYTES;
 constexpr int OFF_SMALL = OFF_P0 + P_BYTES;
-constexpr int ATC_SMEM = OFF_SMALL + 8192 + 1024;
+constexpr int ATC_SMEM = OFF_SMALL + 12288 + 1024;
 
 struct Small {
   unsigned long long bar[8];
   uint32_t tmem_base, pad_[3];
   float q256[64], k256[64], v256[64];
   float p256[256];          // exp(s256 - rowmax) for query rows 0..255
-  float s256[256];          // score of key 256 for query rows 0..255 (scaled)
-  float smax[2][2][128];    // [tile][half][row] maxima of the (unscaled->scaled) scores
-  float ssum[2][2][128];    // [tile][half][row] exp sums
-  float ptail[260];         // tail warp: probabilities of query 256
+  float s256[256];          // scaled score of key 256 for query rows 0..255
+  float tsc[260];           // scaled scores of query 256 against keys 0..256 -> probabilities
+  float smax[2][4][128];    // [tile][column quarter][row]
+  float ssum[2][4][128];
 };
+static_assert(sizeof(Small) <= 12288, "Small");
 
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {   // byte offset inside a SW128 tile
   return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
@@ -69,7 +76,38 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 64-long dot product of an fp32 vector in smem with one row of a swizzled bf16 tile
+__device__ __forceinline__ float dot64(const uint8_t* tile, int row, const float* vec) {
+  float d = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(tile + sw128(row, c));
+    const float4 a = *reinterpret_cast<const float4*>(vec + c * 8);
+    const float4 b = *reinterpret_cast<const float4*>(vec + c * 8 + 4);
+    d += a.x * bf16lo(u.x) + a.y * bf16hi(u.x) + a.z * bf16lo(u.y) + a.w * bf16hi(u.y) +
+         b.x * bf16lo(u.z) + b.y * bf16hi(u.z) + b.z * bf16lo(u.w) + b.w * bf16hi(u.w);
+  }
+  return d;
+}
 
+// FULL: S >= 256, i.e. all 256 tensor-core key columns are valid (no masking in the inner loops)
+template <bool FULL>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attn_vit_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __restrict__ qkv,
                    bf16* __restrict__ out, int S, int H, int C) {
@@ -81,44 +119,43 @@ attn_vit_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __r
   Small* sm = reinterpret_cast<Small*>(smem + OFF_SMALL);
   const uint32_t bar0 = sbase + OFF_SMALL + (uint32_t)offsetof(Small, bar);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  enum { B_LOAD = 0, B_S0 = 1, B_S1 = 2, B_P0 = 3, B_P1 = 4, B_O0 = 5, B_O1 = 6, B_KTAIL = 7 };
+  enum { B_LOAD = 0, B_S0 = 1, B_S1 = 2, B_P0 = 3, B_P1 = 4, B_O0 = 5, B_O1 = 6, B_TAIL = 7 };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % H, n = blockIdx.x / H;
   const long long row0 = (long long)n * S;                 // first token row of this frame
   const int ld = 3 * C;
+  const bool key256 = S > 256;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == SM_WARPS && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     mbar_init(BAR(B_LOAD), 1);
     mbar_init(BAR(B_S0), 1); mbar_init(BAR(B_S1), 1);
-    mbar_init(BAR(B_P0), 256); mbar_init(BAR(B_P1), 256);
+    mbar_init(BAR(B_P0), SM_THREADS); mbar_init(BAR(B_P1), SM_THREADS);
     mbar_init(BAR(B_O0), 1); mbar_init(BAR(B_O1), 1);
-    mbar_init(BAR(B_KTAIL), 1);
+    mbar_init(BAR(B_TAIL), SM_THREADS);
     mbar_fence_init();
   }
-  if (warp == 9) {
+  if (warp == SM_WARPS + 1) {
     tmem_alloc(sbase + OFF_SMALL + (uint32_t)offsetof(Small, tmem_base), 512);
-    // token 256 of q, k, v -> fp32 scalars in smem (lanes 0..31 x 2 values each)
+    // token 256 of q, k, v -> fp32 scalars in smem (2 values per lane)
     const bf16* r = qkv + (row0 + 256) * ld + h * 64;
-    const bool have = S > 256;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int d = lane * 2 + j;
-      sm->q256[d] = have ? __bfloat162float(r[d]) : 0.f;
-      sm->k256[d] = have ? __bfloat162float(r[C + d]) : 0.f;
-      sm->v256[d] = have ? __bfloat162float(r[2 * C + d]) : 0.f;
+      sm->q256[d] = key256 ? __bfloat162float(r[d]) : 0.f;
+      sm->k256[d] = key256 ? __bfloat162float(r[C + d]) : 0.f;
+      sm->v256[d] = key256 ? __bfloat162float(r[2 * C + d]) : 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm->tmem_base;
-  const bool key256 = S > 256;
   constexpr float SCALE = 0.125f;
   constexpr float LOG2E = 1.4426950408889634f;
 
-  if (warp == 8) {
+  if (warp == SM_WARPS) {
     if (lane == 0) {
       // ---------------- TMA + MMA issue ----------------
       mbar_arrive_expect_tx(BAR(B_LOAD), 3 * TILE_BYTES);
@@ -153,110 +190,97 @@ attn_vit_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __r
         tc_commit(BAR(B_O0 + t));
       }
     }
-  } else if (warp == 9) {
-    // ---------------- tail warp: query row 256 on CUDA cores ----------------
+  } else if (warp == SM_WARPS + 1) {
+    // ---------------- tail warp: query row 256 (scores come from the softmax threads) ----------------
     if (key256) {
-      mbar_wait(BAR(B_LOAD), 0);
+      mbar_wait(BAR(B_TAIL), 0);
+      if (lane == 0) {
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) d += sm->q256[c] * sm->k256[c];
+        sm->tsc[256] = bf16r(d) * SCALE;
+      }
+      __syncwarp();
       float sc[9];
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
-        const int j = lane + 32 * i;               // key index, 0..287 (valid < 257)
-        float d = 0.f;
-        if (j < 256) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 u = *reinterpret_cast<const uint4*>(smem + OFF_K + sw128(j, c));
-            const float* q = sm->q256 + c * 8;
-            d += q[0] * bf16lo(u.x) + q[1] * bf16hi(u.x) + q[2] * bf16lo(u.y) + q[3] * bf16hi(u.y) +
-                 q[4] * bf16lo(u.z) + q[5] * bf16hi(u.z) + q[6] * bf16lo(u.w) + q[7] * bf16hi(u.w);
-          }
-        } else if (j == 256) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) d += sm->q256[c] * sm->k256[c];
-        }
-        sc[i] = (j <= 256) ? bf16r(d) * SCALE : -INFINITY;
+        const int j = lane + 32 * i;
+        sc[i] = (j <= 256) ? sm->tsc[j] : -INFINITY;
         mx = fmaxf(mx, sc[i]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(B_KTAIL));    // K tile no longer needed by this warp
       mx = warp_max(mx);
       float sum = 0.f;
+      __syncwarp();
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         const int j = lane + 32 * i;
-        const float p = (j <= 256) ? exp2f((sc[i] - mx) * LOG2E) : 0.f;
+        const float p = (j <= 256) ? ex2_approx((sc[i] - mx) * LOG2E) : 0.f;
         sum += p;
-        if (j <= 256) sm->ptail[j] = bf16r(p);
+        if (j <= 256) sm->tsc[j] = bf16r(p);
       }
       sum = warp_sum(sum);
       __syncwarp();
-      // out[d], d = 2*lane, 2*lane+1
+      // out[d], d = 2*lane, 2*lane+1: 8 keys per iteration keep the smem loads pipelined
       float o0 = 0.f, o1 = 0.f;
       const int ch = lane >> 2, wi = (lane & 3) * 4;   // 16-byte chunk and byte offset of the pair
+#pragma unroll 8
       for (int j = 0; j < 256; ++j) {
         const uint32_t v = *reinterpret_cast<const uint32_t*>(smem + OFF_V + sw128(j, ch) + wi);
-        const float p = sm->ptail[j];
+        const float p = sm->tsc[j];
         o0 += p * bf16lo(v);
         o1 += p * bf16hi(v);
       }
-      o0 += sm->ptail[256] * sm->v256[2 * lane];
-      o1 += sm->ptail[256] * sm->v256[2 * lane + 1];
+      o0 += sm->tsc[256] * sm->v256[2 * lane];
+      o1 += sm->tsc[256] * sm->v256[2 * lane + 1];
       const float inv = 1.0f / sum;
       *reinterpret_cast<uint32_t*>(out + (row0 + 256) * C + h * 64 + 2 * lane) =
           pack_bf16x2(o0 * inv, o1 * inv);
-    } else if (lane == 0) {
-      mbar_arrive(BAR(B_KTAIL));
     }
   } else {
     // ---------------- softmax / epilogue warps ----------------
-    const int q4 = warp & 3, hf = warp >> 2;
+    const int q4 = warp & 3, cq = warp >> 2;         // TMEM lane quarter, column quarter
     const int r = q4 * 32 + lane;                    // row inside the 128-row tile
     mbar_wait(BAR(B_LOAD), 0);
-    {
-      // score of key 256 for query row (hf*128 + r): one 64-long dot product out of the Q tile
-      const int qr = hf * 128 + r;
-      float d = 0.f;
-      if (key256) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = *reinterpret_cast<const uint4*>(smem + OFF_Q + sw128(qr, c));
-          const float* k = sm->k256 + c * 8;
-          d += k[0] * bf16lo(u.x) + k[1] * bf16hi(u.x) + k[2] * bf16lo(u.y) + k[3] * bf16hi(u.y) +
-               k[4] * bf16lo(u.z) + k[5] * bf16hi(u.z) + k[6] * bf16lo(u.w) + k[7] * bf16hi(u.w);
-        }
-      }
-      sm->s256[qr] = key256 ? bf16r(d) * SCALE : -INFINITY;
+    if (key256) {
+      // one 64-long dot product per thread: 256 x (Q row . k256) and 256 x (q256 . K row)
+      const int tix = threadIdx.x;
+      if (tix < 256) sm->s256[tix] = bf16r(dot64(smem + OFF_Q, tix, sm->k256)) * SCALE;
+      else sm->tsc[tix - 256] = bf16r(dot64(smem + OFF_K, tix - 256, sm->q256)) * SCALE;
+    } else if (threadIdx.x < 256) {
+      sm->s256[threadIdx.x] = -INFINITY;
     }
+    mbar_arrive(BAR(B_TAIL));
 #pragma unroll 1
     for (int t = 0; t < 2; ++t) {
-      const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + t * 256 + hf * 128;
-      const int n_valid = min(256, S) - hf * 128;    // valid key columns in this half (<= 128)
+      const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + t * 256 + cq * 64;
+      const int n_valid = FULL ? 64 : max(0, min(64, S - cq * 64));
       mbar_wait(BAR(B_S0 + t), 0);
       tc_fence_after();
-      // pass 1: row maximum over this half
+      // pass 1: row maximum over this column quarter
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(taddr + c * 32, v);
         tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+          if (FULL || c * 32 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
       }
-      sm->smax[t][hf][r] = bf16r(mx) * SCALE;           // rounding and scaling are monotonic
-      named_bar_sync(1, 256);
-      const float m = fmaxf(fmaxf(sm->smax[t][0][r], sm->smax[t][1][r]), sm->s256[t * 128 + r]);
-      if (t == 1) mbar_wait(BAR(B_KTAIL), 0);        // P1 overwrites the Q|K region
-      // pass 2: p = exp(s - m) -> bf16 -> smem (K-major SW128 tile, 4 K-blocks of 64 keys)
-      const uint32_t pbase = (t == 0 ? OFF_P0 : OFF_Q);
+      sm->smax[t][cq][r] = bf16r(mx) * SCALE;        // rounding and scaling are monotonic
+      named_bar_sync(1, SM_THREADS);                 // also orders the Q|K reads above before P1 writes
+      const float m = fmaxf(fmaxf(fmaxf(sm->smax[t][0][r], sm->smax[t][1][r]),
+                                  fmaxf(sm->smax[t][2][r], sm->smax[t][3][r])),
+                            sm->s256[t * 128 + r]);
+      // pass 2: p = exp(s - m) -> bf16 -> smem (K-major SW128 tile; column quarter cq = K-block cq)
+      const uint32_t pbase = (t == 0 ? OFF_P0 : OFF_Q) + cq * 16384;
       const float mb = m * LOG2E;
-      if (hf == 0) sm->p256[t * 128 + r] = key256 ? exp2f(sm->s256[t * 128 + r] * LOG2E - mb) : 0.f;
+      if (cq == 0) sm->p256[t * 128 + r] = key256 ? ex2_approx(sm->s256[t * 128 + r] * LOG2E - mb) : 0.f;
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld_32x32(taddr + c * 32, v);
@@ -265,59 +289,58 @@ attn_vit_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __r
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const uint32_t s2 = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          float p0 = exp2f(bf16lo(s2) * (SCALE * LOG2E) - mb);
-          float p1 = exp2f(bf16hi(s2) * (SCALE * LOG2E) - mb);
-          if (c * 32 + 2 * j >= n_valid) p0 = 0.f;
-          if (c * 32 + 2 * j + 1 >= n_valid) p1 = 0.f;
+          float p0 = ex2_approx(fmaf(bf16lo(s2), SCALE * LOG2E, -mb));
+          float p1 = ex2_approx(fmaf(bf16hi(s2), SCALE * LOG2E, -mb));
+          if (!FULL) {
+            if (c * 32 + 2 * j >= n_valid) p0 = 0.f;
+            if (c * 32 + 2 * j + 1 >= n_valid) p1 = 0.f;
+          }
           sum += p0 + p1;
           pk[j] = pack_bf16x2(p0, p1);
         }
-        const int key0 = hf * 128 + c * 32;          // first key of this chunk
-        const int kb = key0 >> 6, ch0 = (key0 & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(smem + pbase + kb * 16384 + sw128(r, ch0 + q)) =
+          *reinterpret_cast<uint4*>(smem + pbase + sw128(r, c * 4 + q)) =
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
-      sm->ssum[t][hf][r] = sum;
+      sm->ssum[t][cq][r] = sum;
       // generic-proxy smem writes must be visible to the tensor core (async proxy)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(BAR(B_P0 + t));
     }
-    // ---------------- epilogue: O / sum (+ key 256), 32 columns per thread ----------------
+    // ---------------- epilogue: O / sum (+ key 256), 16 columns per thread ----------------
 #pragma unroll 1
     for (int t = 0; t < 2; ++t) {
       mbar_wait(BAR(B_O0 + t), 0);
       tc_fence_after();
-      uint32_t v[32];
+      uint32_t v[16];
       __syncwarp();
-      tmem_ld_32x32(tmem + ((uint32_t)(q4 * 32) << 16) + t * 256 + hf * 32, v);
+      tmem_ld_32x16(tmem + ((uint32_t)(q4 * 32) << 16) + t * 256 + cq * 16, v);
       tc_wait_ld();
       const int qr = t * 128 + r;
       if (qr < S) {
         const float p256 = sm->p256[qr];
-        const float total = sm->ssum[t][0][r] + sm->ssum[t][1][r] + p256;
+        const float total = sm->ssum[t][0][r] + sm->ssum[t][1][r] + sm->ssum[t][2][r] + sm->ssum[t][3][r] + p256;
         const float inv = 1.0f / total;
         const float pb = bf16r(p256);
-        uint32_t o[16];
+        uint32_t o[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = __uint_as_float(v[2 * j]) + pb * sm->v256[hf * 32 + 2 * j];
-          const float b = __uint_as_float(v[2 * j + 1]) + pb * sm->v256[hf * 32 + 2 * j + 1];
+        for (int j = 0; j < 8; ++j) {
+          const float a = __uint_as_float(v[2 * j]) + pb * sm->v256[cq * 16 + 2 * j];
+          const float b = __uint_as_float(v[2 * j + 1]) + pb * sm->v256[cq * 16 + 2 * j + 1];
           o[j] = pack_bf16x2(a * inv, b * inv);
         }
-        bf16* dst = out + (row0 + qr) * C + h * 64 + hf * 32;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        bf16* dst = out + (row0 + qr) * C + h * 64 + cq * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == SM_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -326,7 +349,8 @@ attn_vit_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __r
 }  // namespace
 
 int init_attention_tc_kernels() {
-  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
   return 0;
 }
 
@@ -337,7 +361,10 @@ int launch_attention_vit_tc(const bf16* qkv, bf16* out, int n_frames, int S, int
   VCL_REQUIRE(S >= 129 && S <= 257, "attention_tc: S=%d outside 129..257 (other sizes use the mma.sync kernel)", S);
   CUtensorMap tm;
   if (make_tmap_2d(&tm, qkv, (long long)n_frames * S, 3LL * C, 3LL * C, 256) != 0) return -2;
-  attn_vit_tc_kernel<<<n_frames * H, ATC_THREADS, ATC_SMEM, stream>>>(tm, qkv, out, S, H, C);
+  if (S >= 256)
+    attn_vit_tc_kernel<true><<<n_frames * H, ATC_THREADS, ATC_SMEM, stream>>>(tm, qkv, out, S, H, C);
+  else
+    attn_vit_tc_kernel<false><<<n_frames * H, ATC_THREADS, ATC_SMEM, stream>>>(tm, qkv, out, S, H, C);
   VCL_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return 0;

@@ -84,9 +84,12 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float s) {
 }
 
 template <int NB, int J, int MODE>
-__global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvParams p) {
-  // rows per group; two groups are kept in flight (software pipeline): 2*G*J 128-bit loads per lane
-  constexpr int G = (J == 1) ? 8 : (J == 2 ? 4 : 2);
+__global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const GemvParams p) {
+  // rows per group; two groups are kept in flight (software pipeline): 2*G*J 128-bit loads per lane.
+  // The register budget is 64/thread so that TWO CTAs fit on an SM: the grid is 2 CTAs per SM, and
+  // when a CTA retires the next kernel's CTA (already launched through PDL) starts prefetching
+  // its weights in the freed slot while the neighbour is still streaming.
+  constexpr int G = (J == 1) ? 4 : (J == 2 ? 2 : 1);
   extern __shared__ __align__(16) float part[];  // [GEMV_WARPS][rows_per_cta][NB]
   __shared__ float red[NB][GEMV_WARPS];
   const int K = p.K;
@@ -245,14 +248,14 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvParams 
 
 template <int NB, int J, int MODE>
 int launch_j(GemvParams p, cudaStream_t stream) {
-  int grid = device_num_sms();
+  int grid = 2 * device_num_sms();                  // two resident CTAs per SM (64 registers per thread)
   int R = (p.N + grid - 1) / grid;
   if (R & 1) ++R;                                   // pair modes need whole pairs per CTA
   if (R < 2) R = 2;
   grid = (p.N + R - 1) / R;
   p.rows_per_cta = R;
   const size_t smem = (size_t)GEMV_WARPS * R * NB * sizeof(float);
-  VCL_REQUIRE(smem <= 200 * 1024, "gemv: %d rows per CTA need %zu bytes of shared memory", R, smem);
+  VCL_REQUIRE(smem <= 100 * 1024, "gemv: %d rows per CTA need %zu bytes of shared memory", R, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMV_THREADS);
@@ -296,7 +299,7 @@ int launch_mode(int B, const GemvParams& p, cudaStream_t stream) {
 
 template <int NB, int MODE>
 int init_nb() {
-  const int cap = 200 * 1024;
+  const int cap = 100 * 1024;
   VCL_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<NB, 1, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
   VCL_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<NB, 2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
   VCL_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<NB, 3, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
