@@ -117,13 +117,31 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference path) on a bounded sample
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(model="7b", t_frames=2, l_layers=1, dec_steps=2, dtype=torch.bfloat16):
+def _fastest_cpu_dtype():
+    """bf16 is only quick on hosts with AMX/AVX512-BF16; otherwise fp32 GEMMs are far faster."""
+    best, best_t = torch.float32, None
+    for dt in (torch.float32, torch.bfloat16):
+        a = torch.randn(1024, 1024).to(dt); b = torch.randn(1024, 1024).to(dt)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ b
+        t = time.perf_counter() - t0
+        if best_t is None or t < best_t:
+            best, best_t = dt, t
+    return best
+
+
+def cpu_sample(model="7b", t_frames=2, l_layers=1, dec_steps=2, dtype=None):
     """Times oracle/vcl_oracle.py on the host: the reference's CLIP as it executes it (all 24 layers)
     on t_frames frames, the reference pool on a full [100,256,1024] tensor, and l_layers full-width
     LLaMA layers for a 448-token prefill (logits for all positions, as the reference computes them)
-    plus dec_steps cached steps; extrapolated linearly in frames / layers / steps."""
+    plus dec_steps cached steps; extrapolated linearly in frames / layers / steps. The dtype is the
+    faster of fp32 / bf16 on this host (stated in the sample)."""
     from oracle import vcl_oracle as O
     torch.set_num_threads(os.cpu_count())
+    if dtype is None:
+        dtype = _fastest_cpu_dtype()
     m = MODELS[model]
     ccfg = O.ClipCfg()
     lcfg = O.LlmCfg(hidden=m["hidden"], inter=m["inter"], heads=m["heads"], layers=l_layers)
@@ -163,6 +181,7 @@ def cpu_sample(model="7b", t_frames=2, l_layers=1, dec_steps=2, dtype=torch.bflo
     total = clip_full + t_pool + pre_full + dec_full
     return {
         "value": 1.0 / total, "unit": "videos/s", "cores": os.cpu_count(), "kind": "port",
+        "dtype": "bf16" if dtype == torch.bfloat16 else "f32",
         "sample": (f"oracle (port of the reference path) in {str(dtype).split('.')[-1]} on {os.cpu_count()} host threads: "
                    f"24-layer CLIP on {t_frames} frames ({t_clip:.2f}s), pool [100,256,1024] ({t_pool*1e3:.1f}ms), "
                    f"{l_layers} of {L} {model} layers: 448-token prefill with all-position logits ({t_pre:.2f}s), "
@@ -355,7 +374,7 @@ def run_reference(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "videos/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": last["dtype"], "data": "synthetic",
         "config": {"workload": f"configs[1] on the host CPU (oracle port of the reference path), bounded sample "
                                "extrapolated to 100 frames / all layers / 31 decode steps"},
         "cpu_baseline": last,
