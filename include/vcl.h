@@ -154,6 +154,11 @@ long long vcl_launch_count(void);
 int vcl_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                 const void* bias, const void* residual, int64_t ldr, int M, int N, int K, int act,
                 int block_n, void* stream);
+/* same with an explicit thread-block-cluster size along M (1, 2 or 4): the CTAs of a cluster share
+ * each weight tile through TMA multicast */
+int vcl_op_gemm_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                   const void* bias, const void* residual, int64_t ldr, int M, int N, int K, int act,
+                   int block_n, int cluster, void* stream);
 int vcl_op_layernorm(const void* x, void* y, const void* w, const void* b, int rows, int D, float eps,
                      void* stream);
 int vcl_op_rmsnorm(const void* x, void* y, const void* w, int rows, int D, float eps, void* stream);

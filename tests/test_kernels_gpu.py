@@ -203,3 +203,22 @@ def test_st_pool(T, P, C, dt_in, dt_out):
     ulp = ref.float().abs().clamp_min(2 ** -14) * (2 ** -7 if torch.bfloat16 in (dt_in, dt_out) else 2 ** -10)
     assert (diff <= ulp).all(), diff.max().item()
     assert (out == ref).float().mean().item() > 0.98
+
+
+@pytest.mark.parametrize("M,N,K,bn,cl,act", [(448, 1024, 512, 256, 2, vn.ACT_NONE), (448, 1024, 512, 256, 4, vn.ACT_NONE),
+                                             (300, 512, 256, 128, 4, vn.ACT_NONE), (1000, 2048, 1024, 256, 2, vn.ACT_QGELU),
+                                             (448, 22016, 4096, 256, 4, vn.ACT_SWIGLU), (25700, 3072, 1024, 256, 2, vn.ACT_NONE),
+                                             (129, 256, 64, 128, 2, vn.ACT_NONE)])
+def test_gemm_cluster_multicast(M, N, K, bn, cl, act):
+    """TMA-multicast clusters along M (weight tile shared by 2 / 4 CTAs) give the same result."""
+    torch.manual_seed(M + N + K + cl)
+    dev = _dev()
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev).bfloat16()
+    ref, mag = _gemm_ref(a, w, bias, None, act)
+    out = vn.op_gemm(a, w, bias, None, act, bn, cluster=cl)
+    base = vn.op_gemm(a, w, bias, None, act, bn, cluster=1)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 3e-3, _describe(out, ref)
+    assert torch.equal(out, base), _describe(out, base.float())   # same tiles, same order: bit-identical

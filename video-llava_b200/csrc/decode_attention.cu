@@ -27,15 +27,6 @@ namespace {
 constexpr int DA_SPLIT = 4;
 constexpr int DA_THREADS = 256;
 
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // read a float at the same shared-memory offset in CTA `rank` of the cluster
 __device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
   uint32_t addr = smem_u32(local), remote;
@@ -67,7 +58,7 @@ decode_attn_cluster_kernel(const bf16* __restrict__ q, long long q_ld, const bf1
   float* outp = red + 16 * 128;         // [128] this CTA's partial output
   float* stat = outp + 128;             // [0] local max, [1] local sum
   float* scratch = stat + 2;            // [8]
-  const uint32_t rank = cluster_rank();
+  const uint32_t rank = cluster_ctarank();
   const int h = blockIdx.y, b = blockIdx.z;
   const int lo = (int)rank * per;
   const int n_loc = max(0, min(kv_len - lo, per));

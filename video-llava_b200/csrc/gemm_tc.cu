@@ -58,7 +58,11 @@ __device__ __forceinline__ float act_silu(float g) {
   return bf16r(g / (1.0f + __expf(-g)));
 }
 
-template <int BLOCK_N, int ACT>
+// CL = thread-block-cluster size along M (1, 2 or 4). The CL CTAs of a cluster work on CL
+// consecutive M tiles of the SAME N tile: every CTA fetches 1/CL of the weight tile and TMA-multicasts
+// it into all CL shared memories, so a weight byte crosses L2->SM once per cluster instead of once
+// per CTA (the 128x256 tile is L2-bandwidth-limited otherwise, above all for the short-M prefill).
+template <int BLOCK_N, int ACT, int CL>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, bf16* C, long long ldc,
@@ -91,7 +95,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);      // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -104,28 +108,41 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int num_m = (M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m * num_n;
   const int num_k = (K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
+  // cluster-tile = (N tile, group of CL M tiles); this CTA takes M tile `group*CL + rank`
+  const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  const int num_tiles = ((num_m + CL - 1) / CL) * num_n;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
+  constexpr int B_SLICE_ROWS = BLOCK_N / CL;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait(empty_bar(stage), phase ^ 1u);    // slot free in EVERY CTA of the cluster
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
           tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * Cfg::BLOCK_K, m_blk * Cfg::BLOCK_M);
-          tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_b, full_bar(stage), kb * Cfg::BLOCK_K,
-                      n_blk * BLOCK_N);
+          if (CL == 1) {
+            tma_load_2d(a_dst + Cfg::A_BYTES, &tmap_b, full_bar(stage), kb * Cfg::BLOCK_K,
+                        n_blk * BLOCK_N);
+          } else {
+            // my slice of the weight tile, delivered to the same offset in all CL shared memories
+            tma_load_2d_mc(a_dst + Cfg::A_BYTES + cta_rank * B_SLICE_ROWS * 128, &tmap_b,
+                           full_bar(stage), kb * Cfg::BLOCK_K, n_blk * BLOCK_N + cta_rank * B_SLICE_ROWS,
+                           MC_MASK);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -138,7 +155,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -153,7 +170,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             // advance 16 bf16 = 32 B along K inside the swizzle span: +2 in the (addr >> 4) field
             tc_mma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));                // smem slot free once these MMAs retire
+          // smem slot free once these MMAs retire; with a cluster, tell every CTA that multicasts here
+          if (CL == 1) tc_commit(empty_bar(stage));
+          else tc_commit_mc(empty_bar(stage), MC_MASK);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));                    // accumulator complete -> epilogue
@@ -174,8 +193,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int n_mine = (c_begin + PER <= CH) ? PER : (CH > c_begin ? CH - c_begin : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
       const int row = m_blk * Cfg::BLOCK_M + q4 * 32 + lane;
       const bool row_ok = row < M;
       const int colbase = n_blk * BLOCK_N + c_begin * 32;
@@ -294,6 +313,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // nobody exits while a peer may still multicast / signal into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -350,30 +370,53 @@ int device_num_sms() {
   return g_num_sms;
 }
 
-template <int BLOCK_N, int ACT>
+template <int BLOCK_N, int ACT, int CL>
 static int launch_one(const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_bf16_tn_kernel<BLOCK_N, ACT>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, ACT, CL>;
   CUtensorMap ta, tb;
   if (make_tmap_2d(&ta, g.A, g.M, g.K, g.lda, Cfg::BLOCK_M) != 0) return -2;
-  if (make_tmap_2d(&tb, g.W, g.N, g.K, g.ldw, BLOCK_N) != 0) return -2;
-  const int num_tiles = ((g.M + 127) / 128) * ((g.N + BLOCK_N - 1) / BLOCK_N);
-  int grid = num_tiles < device_num_sms() ? num_tiles : device_num_sms();
-  if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
-  kern<<<grid, 384, Cfg::SMEM_BYTES, stream>>>(ta, tb, g.C, g.ldc, g.bias, g.residual, g.ldr, g.M,
-                                              g.N, g.K);
-  VCL_CUDA_OK(cudaGetLastError());
+  if (make_tmap_2d(&tb, g.W, g.N, g.K, g.ldw, BLOCK_N / CL) != 0) return -2;
+  const int num_m = (g.M + 127) / 128;
+  const int num_tiles = ((num_m + CL - 1) / CL) * ((g.N + BLOCK_N - 1) / BLOCK_N);   // cluster-tiles
+  int clusters = device_num_sms() / CL;
+  if (CL == 4) clusters -= 4;            // GPC boundaries strand ~16 SMs for 4-CTA clusters
+  if (clusters > num_tiles) clusters = num_tiles;
+  if (g.max_ctas > 0 && clusters * CL > g.max_ctas) clusters = g.max_ctas / CL > 0 ? g.max_ctas / CL : 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.C, (long long)g.ldc, g.bias, g.residual,
+                                 (long long)g.ldr, g.M, g.N, g.K));
   count_launches(1);
   return 0;
 }
 
+template <int BLOCK_N, int ACT>
+static int launch_cl(const GemmArgs& g, int cl, cudaStream_t stream) {
+  if (BLOCK_N >= 128) {   // multicast slices must stay whole 8-row swizzle groups and >= 32 rows
+    if (cl == 4) return launch_one<BLOCK_N, ACT, (BLOCK_N >= 128 ? 4 : 1)>(g, stream);
+    if (cl == 2) return launch_one<BLOCK_N, ACT, (BLOCK_N >= 128 ? 2 : 1)>(g, stream);
+  }
+  return launch_one<BLOCK_N, ACT, 1>(g, stream);
+}
+
 template <int BLOCK_N>
-static int launch_act(const GemmArgs& g, cudaStream_t stream) {
+static int launch_act(const GemmArgs& g, int cl, cudaStream_t stream) {
   switch (g.act) {
-    case ACT_NONE: return launch_one<BLOCK_N, ACT_NONE>(g, stream);
-    case ACT_QGELU: return launch_one<BLOCK_N, ACT_QGELU>(g, stream);
-    case ACT_GELU: return launch_one<BLOCK_N, ACT_GELU>(g, stream);
-    case ACT_SWIGLU: return launch_one<BLOCK_N, ACT_SWIGLU>(g, stream);
+    case ACT_NONE: return launch_cl<BLOCK_N, ACT_NONE>(g, cl, stream);
+    case ACT_QGELU: return launch_cl<BLOCK_N, ACT_QGELU>(g, cl, stream);
+    case ACT_GELU: return launch_cl<BLOCK_N, ACT_GELU>(g, cl, stream);
+    case ACT_SWIGLU: return launch_cl<BLOCK_N, ACT_SWIGLU>(g, cl, stream);
   }
   set_last_error("gemm: unknown activation %d", g.act);
   return -1;
@@ -381,9 +424,17 @@ static int launch_act(const GemmArgs& g, cudaStream_t stream) {
 
 template <int BLOCK_N, int ACT>
 static int init_one() {
-  VCL_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, ACT>,
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, ACT, 1>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    GemmCfg<BLOCK_N>::SMEM_BYTES));
+  if (BLOCK_N >= 128) {
+    VCL_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, ACT, (BLOCK_N >= 128 ? 2 : 1)>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmCfg<BLOCK_N>::SMEM_BYTES));
+    VCL_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BLOCK_N, ACT, (BLOCK_N >= 128 ? 4 : 1)>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmCfg<BLOCK_N>::SMEM_BYTES));
+  }
   return 0;
 }
 template <int BLOCK_N>
@@ -411,19 +462,39 @@ int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
   VCL_REQUIRE(g.bias == nullptr || ((uintptr_t)g.bias % 16) == 0, "gemm: bias alignment");
   VCL_REQUIRE(!(g.act == ACT_SWIGLU && g.residual != nullptr), "gemm: swiglu takes no residual");
   int bn = g.block_n;
+  int cl = g.cluster;
   if (bn == 0) {
-    // pick the widest tile that still gives every SM at least one tile (wave quantisation)
+    // Tile / cluster choice, from the block_n x cluster sweep on B200 (profiles/r01_gemm_sweep.txt):
+    //  * many M tiles (ViT, batched prefill): 128x256 tiles, pairs of CTAs sharing each weight tile;
+    //  * few M tiles (single-clip prefill, M = 448): the weight stream dominates L2->SM traffic, so
+    //    all M tiles of an N tile form one cluster (multicast x4) when there are enough tiles to fill
+    //    the machine twice, else narrower tiles without a cluster to get more CTAs in flight;
+    //  * one M tile (decode with B > 4): the narrowest tile that still gives every SM work.
     const int sms = device_num_sms();
     const long long mt = (g.M + 127) / 128;
-    bn = 256;
-    while (bn > 32 && (g.N % bn != 0 || mt * (g.N / bn) < sms)) bn >>= 1;
-    if (g.N % bn != 0) bn = 32;
+    int auto_cl = 1;
+    if (mt >= 16 && g.N % 256 == 0) {
+      bn = 256; auto_cl = 2;
+    } else if (mt >= 2) {
+      const int mcl = mt >= 4 ? 4 : 2;
+      if (g.N % 256 == 0 && mt * (g.N / 256) >= 2 * sms) { bn = 256; auto_cl = mcl; }
+      else if (g.N % 128 == 0 && mt * (g.N / 128) >= 2 * sms) { bn = 128; auto_cl = mcl; }
+      else if (g.N % 128 == 0) { bn = 128; }
+      else { bn = (g.N % 64 == 0) ? 64 : 32; }
+    } else {
+      bn = 256;
+      while (bn > 32 && (g.N % bn != 0 || mt * (g.N / bn) < sms)) bn >>= 1;
+      if (g.N % bn != 0) bn = 32;
+    }
+    if (cl == 0) cl = auto_cl;
   }
+  if (cl == 0) cl = 1;
+  VCL_REQUIRE(cl == 1 || cl == 2 || cl == 4, "gemm: cluster must be 1, 2 or 4 (got %d)", cl);
   switch (bn) {
-    case 256: return launch_act<256>(g, stream);
-    case 128: return launch_act<128>(g, stream);
-    case 64: return launch_act<64>(g, stream);
-    case 32: return launch_act<32>(g, stream);
+    case 256: return launch_act<256>(g, cl, stream);
+    case 128: return launch_act<128>(g, cl, stream);
+    case 64: return launch_act<64>(g, 1, stream);
+    case 32: return launch_act<32>(g, 1, stream);
   }
   set_last_error("gemm: unsupported block_n %d", bn);
   return -1;

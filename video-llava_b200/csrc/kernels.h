@@ -28,6 +28,7 @@ struct GemmArgs {
   int M = 0, N = 0, K = 0;
   int act = ACT_NONE;
   int block_n = 0;     // 0 = choose
+  int cluster = 0;     // CTAs per cluster along M sharing multicast weight tiles: 0/1, 2 or 4
   int max_ctas = 0;    // 0 = one per SM
 };
 int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);

@@ -364,8 +364,9 @@ namespace {
 
 int gemm(const bf16* A, long long lda, const bf16* W, long long ldw, bf16* C, long long ldc,
          const bf16* bias, const bf16* res, long long ldr, int M, int N, int K, int act,
-         cudaStream_t st, int block_n = 0) {
+         cudaStream_t st, int block_n = 0, int cluster = 0) {
   GemmArgs g;
+  g.cluster = cluster;
   g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.C = C; g.ldc = ldc; g.bias = bias;
   g.residual = res; g.ldr = ldr; g.M = M; g.N = N; g.K = K; g.act = act; g.block_n = block_n;
   return launch_gemm_bf16_tn(g, st);
@@ -658,6 +659,12 @@ long long vcl_launch_count(void) { return launch_count(); }
 int vcl_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                 const void* bias, const void* residual, int64_t ldr, int M, int N, int K, int act,
                 int block_n, void* stream) {
+  return vcl_op_gemm_ex(A, lda, W, ldw, C, ldc, bias, residual, ldr, M, N, K, act, block_n, 0, stream);
+}
+
+int vcl_op_gemm_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                   const void* bias, const void* residual, int64_t ldr, int M, int N, int K, int act,
+                   int block_n, int cluster, void* stream) {
   if (check_device() != 0) return -2;
   static bool inited = false;
   if (!inited) {
@@ -666,7 +673,7 @@ int vcl_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C,
   }
   return gemm(reinterpret_cast<const bf16*>(A), lda, reinterpret_cast<const bf16*>(W), ldw,
               reinterpret_cast<bf16*>(C), ldc, reinterpret_cast<const bf16*>(bias),
-              reinterpret_cast<const bf16*>(residual), ldr, M, N, K, act, as_stream(stream), block_n);
+              reinterpret_cast<const bf16*>(residual), ldr, M, N, K, act, as_stream(stream), block_n, cluster);
 }
 
 int vcl_op_layernorm(const void* x, void* y, const void* w, const void* b, int rows, int D, float eps,

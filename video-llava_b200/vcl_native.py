@@ -62,6 +62,8 @@ _SIGNATURES = {
     "vcl_launch_count": (ctypes.c_longlong, []),
     "vcl_op_gemm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                             c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vcl_op_gemm_ex": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                               c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vcl_op_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "vcl_op_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "vcl_op_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -130,15 +132,15 @@ def st_pool(features: torch.Tensor, n_temporal: int = 100, out_dtype: torch.dtyp
     return out
 
 
-def op_gemm(a, w, bias=None, residual=None, act=ACT_NONE, block_n=0, out=None):
+def op_gemm(a, w, bias=None, residual=None, act=ACT_NONE, block_n=0, out=None, cluster=0):
     M, K = a.shape
     N = w.shape[0]
     n_out = N // 2 if act == ACT_SWIGLU else N
     if out is None:
         out = torch.empty(M, n_out, dtype=torch.bfloat16, device=a.device)
-    check(lib().vcl_op_gemm(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), ptr(bias),
-                            ptr(residual), residual.stride(0) if residual is not None else 0, M, N, K,
-                            act, block_n, cur_stream()))
+    check(lib().vcl_op_gemm_ex(ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), ptr(bias),
+                               ptr(residual), residual.stride(0) if residual is not None else 0, M, N, K,
+                               act, block_n, cluster, cur_stream()))
     return out
 
 
