@@ -24,6 +24,7 @@
 #include "kernels.h"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace vcl {
 
@@ -486,7 +487,9 @@ int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
       while (bn > 32 && (g.N % bn != 0 || mt * (g.N / bn) < sms)) bn >>= 1;
       if (g.N % bn != 0) bn = 32;
     }
-    if (cl == 0) cl = auto_cl;
+    static const int forced_cl = getenv("VCL_GEMM_CLUSTER") ? atoi(getenv("VCL_GEMM_CLUSTER")) : 0;   // A/B switch
+    if (cl == 0) cl = forced_cl ? forced_cl : auto_cl;
+    if (forced_cl == 1 && mt >= 2 && mt < 16 && bn == 128 && g.N % 256 == 0 && mt * (g.N / 256) >= sms) bn = 256;
   }
   if (cl == 0) cl = 1;
   VCL_REQUIRE(cl == 1 || cl == 2 || cl == 4, "gemm: cluster must be 1, 2 or 4 (got %d)", cl);

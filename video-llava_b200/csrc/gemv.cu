@@ -28,6 +28,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace vcl {
 
 namespace {
@@ -248,7 +250,10 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const GemvParams 
 
 template <int NB, int J, int MODE>
 int launch_j(GemvParams p, cudaStream_t stream) {
-  int grid = 2 * device_num_sms();                  // two resident CTAs per SM (64 registers per thread)
+  // CTAs per SM in the grid (two fit: 64 registers per thread). VCL_GEMV_CTAS_PER_SM=1 leaves the
+  // second slot to the NEXT kernel's CTAs, which PDL lets start prefetching weights early.
+  static const int per_sm = getenv("VCL_GEMV_CTAS_PER_SM") ? atoi(getenv("VCL_GEMV_CTAS_PER_SM")) : 2;
+  int grid = (per_sm > 0 ? per_sm : 2) * device_num_sms();
   int R = (p.N + grid - 1) / grid;
   if (R & 1) ++R;                                   // pair modes need whole pairs per CTA
   if (R < 2) R = 2;
