@@ -86,7 +86,7 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float s) {
 }
 
 template <int NB, int J, int MODE>
-__global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const GemvParams p) {
+__global__ void __launch_bounds__(GEMV_THREADS, (NB * J <= 4) ? 2 : 1) gemv_kernel(const GemvParams p) {
   // rows per group; two groups are kept in flight (software pipeline): 2*G*J 128-bit loads per lane.
   // The register budget is 64/thread so that TWO CTAs fit on an SM: the grid is 2 CTAs per SM, and
   // when a CTA retires the next kernel's CTA (already launched through PDL) starts prefetching
@@ -171,6 +171,18 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const GemvParams 
   }
 
   // ---------------- main loop over this CTA's rows: two groups of G rows in flight ----------------
+  // single-clip decode: keep the activation chunks unpacked (fp32) so the inner loop only unpacks
+  // the weights (8 instead of 16 conversion instructions per 16-byte chunk)
+  constexpr bool XF = (NB == 1 && J <= 3);
+  float xf[XF ? J : 1][8];
+  if (XF) {
+#pragma unroll
+    for (int j = 0; j < (XF ? J : 1); ++j) {
+      const uint4 u = xv[0][j];
+      xf[j][0] = bf16lo(u.x); xf[j][1] = bf16hi(u.x); xf[j][2] = bf16lo(u.y); xf[j][3] = bf16hi(u.y);
+      xf[j][4] = bf16lo(u.z); xf[j][5] = bf16hi(u.z); xf[j][6] = bf16lo(u.w); xf[j][7] = bf16hi(u.w);
+    }
+  }
   auto process = [&](int g0, const uint4 (&wv)[G][J]) {
     float acc[G][NB];
 #pragma unroll
@@ -179,7 +191,17 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_kernel(const GemvParams 
       for (int b = 0; b < NB; ++b) {
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < J; ++j) s = dot8(wv[g][j], xv[b][j], s);
+        for (int j = 0; j < J; ++j) {
+          if (XF) {
+            const uint4 w = wv[g][j];
+            s = fmaf(bf16lo(w.x), xf[XF ? j : 0][0], s); s = fmaf(bf16hi(w.x), xf[XF ? j : 0][1], s);
+            s = fmaf(bf16lo(w.y), xf[XF ? j : 0][2], s); s = fmaf(bf16hi(w.y), xf[XF ? j : 0][3], s);
+            s = fmaf(bf16lo(w.z), xf[XF ? j : 0][4], s); s = fmaf(bf16hi(w.z), xf[XF ? j : 0][5], s);
+            s = fmaf(bf16lo(w.w), xf[XF ? j : 0][6], s); s = fmaf(bf16hi(w.w), xf[XF ? j : 0][7], s);
+          } else {
+            s = dot8(wv[g][j], xv[b][j], s);
+          }
+        }
         acc[g][b] = s;
       }
 #pragma unroll
@@ -253,7 +275,8 @@ int launch_j(GemvParams p, cudaStream_t stream) {
   // CTAs per SM in the grid (two fit: 64 registers per thread). VCL_GEMV_CTAS_PER_SM=1 leaves the
   // second slot to the NEXT kernel's CTAs, which PDL lets start prefetching weights early.
   static const int per_sm = getenv("VCL_GEMV_CTAS_PER_SM") ? atoi(getenv("VCL_GEMV_CTAS_PER_SM")) : 2;
-  int grid = (per_sm > 0 ? per_sm : 2) * device_num_sms();
+  // batches whose activation registers do not fit the 64-register budget run one CTA per SM
+  int grid = ((NB * J <= 4) ? (per_sm > 0 ? per_sm : 2) : 1) * device_num_sms();
   int R = (p.N + grid - 1) / grid;
   if (R & 1) ++R;                                   // pair modes need whole pairs per CTA
   if (R < 2) R = 2;

@@ -97,6 +97,28 @@ int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, c
                             bf16* o, long long o_ld, int B, int H, int head_dim, int s_max,
                             int kv_len, float scale, cudaStream_t stream);
 
+// ---- decode_mega.cu : one whole cached decoding step (B <= 4) as a single persistent kernel ------
+struct MegaLayer { const bf16 *ln1, *wqkv, *wo, *ln2, *wgu, *wd; };
+struct MegaParams {
+  int L, D, F, H, V, s_max;
+  float eps, scale;
+  const MegaLayer* layers;          // device array [L]
+  const bf16 *embed, *norm_w, *lm_head;
+  bf16 *kcache, *vcache;            // [L][B][H][s_max][128]
+  long long cache_layer_elems;
+  const bf16 *cos_t, *sin_t;
+  bf16 *h, *q, *act;                // [B,D], [B,D], [B,F]
+  float *att_stats, *att_part;      // [B,H,4,2], [B,H,4,128]
+  float* logits;                    // [B,V]
+  const int* tok_in; long long tok_in_stride;
+  int* tok_out; long long tok_out_stride;
+  int pos;
+  unsigned int* barrier;            // grid-barrier counter (zeroed by the launcher)
+};
+int init_decode_mega_kernels();
+bool decode_mega_supported(int B, int D, int F, int V);
+int launch_decode_mega(const MegaParams& p, int B, cudaStream_t stream);
+
 // ---- gemv.cu : decode-time weight streaming (M = B <= 8 rows) ------------------------------------
 struct GemvArgs {
   const bf16* x = nullptr; long long ldx = 0;   // [B, K]
@@ -116,5 +138,16 @@ int launch_gemv_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kc
 int init_gemv_kernels();
 // logits (bf16-rounded, stored fp32) [B, N]
 int launch_gemv_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
+
+// ---- gemv_mma.cu : small-batch (2..16) decode projections on mma.sync, input already normalised ----
+int init_gemv_mma_kernels();
+int launch_gemv_mma_residual(const GemvArgs& g, bf16* out, long long ldo, const bf16* res, long long ldr,
+                             cudaStream_t stream);
+int launch_gemv_mma_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t stream);
+int launch_gemv_mma_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
+                             const bf16* cos_t, const bf16* sin_t, int H, int head_dim, int s_max, int pos,
+                             cudaStream_t stream);
+int launch_gemv_mma_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
+
 
 }  // namespace vcl

@@ -82,6 +82,10 @@ struct vcl_handle {
   bf16 *d_h = nullptr, *d_x = nullptr, *d_q = nullptr, *d_qkv = nullptr, *d_attn = nullptr,
        *d_act = nullptr;
   std::vector<GraphEntry> graphs;
+  MegaLayer* mega_layers = nullptr;            // device copy of the per-layer weight pointers
+  float *att_stats = nullptr, *att_part = nullptr;
+  unsigned int* mega_barrier = nullptr;
+  bool use_mega = true;
   bool force_legacy_attention = false;
 
   size_t cache_layer_elems() const {
@@ -189,8 +193,12 @@ int vcl_create(vcl_handle** out, const vcl_config* c) {
   rc |= init_gemm_kernels();
   rc |= init_attention_kernels();
   rc |= init_attention_tc_kernels();
+  rc |= init_decode_mega_kernels();
+  // the persistent whole-step kernel is correct but (round 1) slower than the per-phase GEMV chain: opt-in
+  h->use_mega = getenv("VCL_MEGAKERNEL") != nullptr && getenv("VCL_NO_MEGAKERNEL") == nullptr;
   h->force_legacy_attention = getenv("VCL_LEGACY_ATTENTION") != nullptr;
   rc |= init_gemv_kernels();
+  rc |= init_gemv_mma_kernels();
 
   const size_t C = c->clip_hidden, F = c->clip_inter;
   const size_t Mv = (size_t)c->max_frames * (h->P + 1);
@@ -224,6 +232,10 @@ int vcl_create(vcl_handle** out, const vcl_config* c) {
   rc |= dalloc(h, &h->d_qkv, Bm * 3 * D);
   rc |= dalloc(h, &h->d_attn, Bm * D);
   rc |= dalloc(h, &h->d_act, Bm * LF);
+  rc |= dalloc(h, &h->att_stats, Bm * c->llm_heads * 4 * 2);
+  rc |= dalloc(h, &h->att_part, Bm * c->llm_heads * 4 * 128);
+  rc |= dalloc(h, &h->mega_barrier, 32 * 17);
+  rc |= dalloc(h, &h->mega_layers, (size_t)(c->llm_layers > 0 ? c->llm_layers : 1));
   if (rc == 0) rc = launch_rope_table(h->rope_cos, h->rope_sin, c->max_seq, 128, c->rope_theta, 0);
   if (rc == 0) {
     cudaError_t e = cudaDeviceSynchronize();
@@ -344,6 +356,15 @@ int vcl_load_llm_weights(vcl_handle* h, const vcl_tensor* tensors, int n) {
                              cudaMemcpyDeviceToDevice));
     if (load_copy(h, m, lp + "mlp.down_proj.weight", &w.wd, 2, D, F)) return -1;
   }
+  {
+    std::vector<MegaLayer> ml(c.llm_layers);
+    for (int l = 0; l < c.llm_layers; ++l) {
+      const LlmLayerW& w = h->ll[l];
+      ml[l] = MegaLayer{w.ln1, w.wqkv, w.wo, w.ln2, w.wgu, w.wd};
+    }
+    if (c.llm_layers > 0)
+      VCL_CUDA_OK(cudaMemcpy(h->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+  }
   VCL_CUDA_OK(cudaDeviceSynchronize());
   h->llm_loaded = true;
   return 0;
@@ -420,6 +441,17 @@ bf16* vc_layer(vcl_handle* h, int l) { return h->vcache + (size_t)l * h->cache_l
 int lm_head_argmax(vcl_handle* h, const bf16* x, long long ldx, int B, float* logits_out,
                    int32_t* tok_out, long long tok_stride, cudaStream_t st) {
   const vcl_config& c = h->cfg;
+  if (B >= 2) {
+    // small batches: normalise the B rows once, then the mma.sync weight-streaming kernel
+    for (int b0 = 0; b0 < B; b0 += 16) {
+      const int nb = B - b0 < 16 ? B - b0 : 16;
+      VCL_TRY(launch_rmsnorm(x + (long long)b0 * ldx, ldx, h->d_x, c.llm_hidden, h->norm_w, nb, c.llm_hidden,
+                             c.rms_eps, st));
+      GemvArgs g;
+      g.x = h->d_x; g.ldx = c.llm_hidden; g.W = h->lm_head; g.B = nb; g.N = c.vocab; g.K = c.llm_hidden;
+      VCL_TRY(launch_gemv_mma_logits(g, h->logits + (size_t)b0 * c.vocab, c.vocab, st));
+    }
+  } else
   for (int b0 = 0; b0 < B; b0 += 4) {
     const int nb = B - b0 < 4 ? B - b0 : 4;
     GemvArgs g;
@@ -495,10 +527,46 @@ int llm_decode_step(vcl_handle* h, const int32_t* tok_in, long long in_stride, i
   const int D = c.llm_hidden, F = c.llm_inter, H = c.llm_heads;
   const float scale = 0.08838834764831845f;
   VCL_REQUIRE(pos >= 0 && pos < c.max_seq, "decode position %d outside the cache (max_seq %d)", pos, c.max_seq);
+  if (h->use_mega && tok_out != nullptr && c.llm_layers > 0 && decode_mega_supported(B, D, F, c.vocab) &&
+      pos + 1 <= 512 && B * H * 4 <= 4 * device_num_sms()) {
+    MegaParams mp = {};
+    mp.L = c.llm_layers; mp.D = D; mp.F = F; mp.H = H; mp.V = c.vocab; mp.s_max = c.max_seq;
+    mp.eps = c.rms_eps; mp.scale = scale;
+    mp.layers = h->mega_layers; mp.embed = h->embed; mp.norm_w = h->norm_w; mp.lm_head = h->lm_head;
+    mp.kcache = h->kcache; mp.vcache = h->vcache; mp.cache_layer_elems = (long long)h->cache_layer_elems();
+    mp.cos_t = h->rope_cos; mp.sin_t = h->rope_sin;
+    mp.h = h->d_h; mp.q = h->d_q; mp.act = h->d_act;
+    mp.att_stats = h->att_stats; mp.att_part = h->att_part; mp.logits = h->logits;
+    mp.tok_in = tok_in; mp.tok_in_stride = in_stride; mp.tok_out = tok_out; mp.tok_out_stride = out_stride;
+    mp.pos = pos; mp.barrier = h->mega_barrier;
+    VCL_TRY(launch_decode_mega(mp, B, st));
+    if (logits_out != nullptr && logits_out != h->logits)
+      VCL_CUDA_OK(cudaMemcpyAsync(logits_out, h->logits, (size_t)B * c.vocab * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
   VCL_TRY(launch_embed_tokens(tok_in, in_stride, h->embed, h->d_h, B, D, c.vocab, st));
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlmLayerW& w = h->ll[l];
-    if (B <= 4) {
+    if (B >= 2 && B <= 16) {
+      GemvArgs g;
+      VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln1, B, D, c.rms_eps, st));
+      g.x = h->d_x; g.ldx = D; g.W = w.wqkv; g.B = B; g.N = 3 * D; g.K = D;
+      VCL_TRY(launch_gemv_mma_qkv_rope(g, h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin,
+                                       H, 128, c.max_seq, pos, st));
+      VCL_TRY(launch_decode_attention(h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, B, H, 128,
+                                      c.max_seq, pos + 1, scale, st));
+      GemvArgs go;
+      go.x = h->d_attn; go.ldx = D; go.W = w.wo; go.B = B; go.N = D; go.K = D;
+      VCL_TRY(launch_gemv_mma_residual(go, h->d_h, D, h->d_h, D, st));
+      VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln2, B, D, c.rms_eps, st));
+      GemvArgs gg;
+      gg.x = h->d_x; gg.ldx = D; gg.W = w.wgu; gg.B = B; gg.N = 2 * F; gg.K = D;
+      VCL_TRY(launch_gemv_mma_swiglu(gg, h->d_act, F, st));
+      GemvArgs gd;
+      gd.x = h->d_act; gd.ldx = F; gd.W = w.wd; gd.B = B; gd.N = D; gd.K = F;
+      VCL_TRY(launch_gemv_mma_residual(gd, h->d_h, D, h->d_h, D, st));
+    } else if (B <= 4) {
       GemvArgs g;
       g.x = h->d_h; g.ldx = D; g.W = w.wqkv; g.B = B; g.N = 3 * D; g.K = D; g.norm_w = w.ln1; g.eps = c.rms_eps;
       VCL_TRY(launch_gemv_qkv_rope(g, h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin,
