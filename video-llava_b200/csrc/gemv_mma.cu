@@ -91,9 +91,10 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemv_mma_kernel(const GmParams 
     float c[NBLK][4];
 #pragma unroll
     for (int nb = 0; nb < NBLK; ++nb) c[nb][0] = c[nb][1] = c[nb][2] = c[nb][3] = 0.f;
-    constexpr int U = 8;                                           // K blocks in flight: 16 loads per lane
+    constexpr int U = 4;                                           // K blocks in flight per lane
     for (int kb = kb0; kb < kb1; kb += U) {
-      uint4 w0[U], w1[U];
+      // weights (HBM) and activation fragments (L1/L2) of U K-blocks are all issued before any MMA
+      uint4 w0[U], w1[U], xa[U], xb[NBLK == 2 ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int k = (kb + u) * 32;
@@ -104,15 +105,19 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemv_mma_kernel(const GmParams 
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int k = (kb + u) * 32;
-        if (kb + u < kb1) {
-          const uint4 xa = x0_ok ? *reinterpret_cast<const uint4*>(xr0 + k) : make_uint4(0, 0, 0, 0);
-          mma16816(c[0], w0[u].x, w1[u].x, w0[u].y, w1[u].y, xa.x, xa.y);
-          mma16816(c[0], w0[u].z, w1[u].z, w0[u].w, w1[u].w, xa.z, xa.w);
-          if (NBLK == 2) {
-            const uint4 xb = x1_ok ? *reinterpret_cast<const uint4*>(xr1 + k) : make_uint4(0, 0, 0, 0);
-            mma16816(c[NBLK - 1], w0[u].x, w1[u].x, w0[u].y, w1[u].y, xb.x, xb.y);
-            mma16816(c[NBLK - 1], w0[u].z, w1[u].z, w0[u].w, w1[u].w, xb.z, xb.w);
-          }
+        const bool ok = kb + u < kb1;
+        xa[u] = (ok && x0_ok) ? __ldg(reinterpret_cast<const uint4*>(xr0 + k)) : make_uint4(0, 0, 0, 0);
+        if (NBLK == 2)
+          xb[NBLK == 2 ? u : 0] = (ok && x1_ok) ? __ldg(reinterpret_cast<const uint4*>(xr1 + k)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        mma16816(c[0], w0[u].x, w1[u].x, w0[u].y, w1[u].y, xa[u].x, xa[u].y);
+        mma16816(c[0], w0[u].z, w1[u].z, w0[u].w, w1[u].w, xa[u].z, xa[u].w);
+        if (NBLK == 2) {
+          const uint4 xq = xb[NBLK == 2 ? u : 0];
+          mma16816(c[NBLK - 1], w0[u].x, w1[u].x, w0[u].y, w1[u].y, xq.x, xq.y);
+          mma16816(c[NBLK - 1], w0[u].z, w1[u].z, w0[u].w, w1[u].w, xq.z, xq.w);
         }
       }
     }
