@@ -132,7 +132,10 @@ def _fastest_cpu_dtype():
     return best
 
 
-def cpu_sample(model="7b", t_frames=2, l_layers=1, dec_steps=2, dtype=None):
+_CPU_WEIGHTS = {}
+
+
+def cpu_sample(model="7b", t_frames=4, l_layers=2, dec_steps=4, dtype=None):
     """Times oracle/vcl_oracle.py on the host: the reference's CLIP as it executes it (all 24 layers)
     on t_frames frames, the reference pool on a full [100,256,1024] tensor, and l_layers full-width
     LLaMA layers for a 448-token prefill (logits for all positions, as the reference computes them)
@@ -147,8 +150,11 @@ def cpu_sample(model="7b", t_frames=2, l_layers=1, dec_steps=2, dtype=None):
     lcfg = O.LlmCfg(hidden=m["hidden"], inter=m["inter"], heads=m["heads"], layers=l_layers)
     t_all = time.perf_counter()
     with torch.no_grad():
-        csd = {k: v.to(dtype) for k, v in O.random_clip_state(ccfg, seed=0, n_layers=24).items()}
-        lsd = O.random_llm_state(lcfg, seed=0, dtype=dtype)
+        key = (model, l_layers, dtype)
+        if key not in _CPU_WEIGHTS:            # random-init weights are built once per process
+            _CPU_WEIGHTS[key] = ({k: v.to(dtype) for k, v in O.random_clip_state(ccfg, seed=0, n_layers=24).items()},
+                                 O.random_llm_state(lcfg, seed=0, dtype=dtype))
+        csd, lsd = _CPU_WEIGHTS[key]
         px = O.preprocess_frames(O.make_frames(0, t_frames)).to(dtype)
         O.clip_hidden_states(csd, ccfg, px[:1], 24)                       # warm-up
         t0 = time.perf_counter(); O.clip_hidden_states(csd, ccfg, px, 24); t_clip = time.perf_counter() - t0

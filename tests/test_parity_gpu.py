@@ -227,3 +227,38 @@ def test_error_behaviour():
         eng.prefill(ids, None, vs)
     with pytest.raises(vn.VclError, match="T=101"):
         vn.st_pool(torch.zeros(101, 4, 8, device=DEV, dtype=torch.float16))
+
+
+@torch.no_grad()
+def test_336px_mlp2x_variant_end_to_end():
+    """SURVEY.md 8f row 2 (LLaVA-1.5 style checkpoints): 336-px tower (P = 576, S = 577, so the ViT
+    attention takes the flash-style kernel), 676 video tokens, mlp2x_gelu projector."""
+    ccfg = O.ClipCfg(hidden=1024, inter=1024, heads=16, layers=3, image=336)
+    lcfg = O.LlmCfg(hidden=512, inter=1024, heads=4, layers=2, proj_type="mlp2x_gelu")
+    csd, lsd = O.random_clip_state(ccfg, seed=5), O.random_llm_state(lcfg, seed=6)
+    frames = O.make_frames(11, 4, size=336)
+    px = O.preprocess_frames(frames).to(DEV)
+    eng = make_engine(clip=ccfg, llm=lcfg, clip_run_layers=2, max_frames=4, max_batch=1, max_seq=800)
+    eng.load_clip(to_dev(csd))
+    eng.load_llm(to_dev(lsd))
+    assert eng.P == 576 and eng.NV == 676
+    hid = eng.clip_encode(px.bfloat16())
+    assert hid.shape == (4, 577, 1024)
+    gold = O.clip_hidden_states(to_dev(csd, torch.float32), ccfg, px, 2)[-1]
+    refb = O.clip_hidden_states(to_dev(csd), ccfg, px.bfloat16(), 2)[-1]
+    _bar(hid, refb, gold, "336px ViT hidden_states[2]")
+    feats = eng.clip_features(torch.as_tensor(frames).to(DEV), torch.float16)      # uint8 path
+    assert feats.shape == (676, 1024) and (feats[4:100] == 0).all()
+    _bar(feats, O.st_pool_torch(refb[:, 1:]), O.st_pool_torch(gold[:, 1:]), "336px pooled features")
+    ids = O.make_prompt_ids(lcfg, 676, seed=2).to(DEV)
+    assert ids.shape == (1, 768)
+    vf = feats[None].float()
+    sd_b, sd_f = to_dev(lsd), to_dev(lsd, torch.float32)
+    _, gold_hs, _ = O.llm_forward(sd_f, lcfg, ids, vf)
+    _, refb_hs, _ = O.llm_forward(sd_b, lcfg, ids, vf.bfloat16())
+    vs = vid_start_of(ids, lcfg)
+    h0, _, _ = eng.prefill(ids, vf, vs, n_layers=0, want_hidden=True, want_token=False)
+    _bar(h0[:, 65:741], refb_hs[0][:, 65:741], gold_hs[0][:, 65:741], "mlp2x_gelu projector rows")
+    h1, _, _ = eng.prefill(ids, vf, vs, n_layers=1, want_hidden=True, want_token=False)
+    _bar(h1, refb_hs[1], gold_hs[1], "336px llm hidden_states[1]")
+    _teacher_forced_check(eng, sd_b, lcfg, ids, vf, 6, "336px / mlp2x_gelu")
