@@ -31,6 +31,7 @@
 
 #include <cudaTypedefs.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 namespace vcl {
 
@@ -346,11 +347,261 @@ attn_vit_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Single-tile variant: one CTA per (frame, head, 128-query tile), TWO CTAs per SM (256 TMEM columns
+// and ~104 KB of shared memory each), so that one CTA's TMA / MMA / barrier latencies overlap the
+// other's softmax. Same arithmetic as above. P (64 KB) re-uses the Q|K region (48 KB) plus one
+// extra 16 KB block once S has been computed and the Q / K rows have been read.
+// ---------------------------------------------------------------------------------------------
+constexpr int T1_SM_WARPS = 8;
+constexpr int T1_SM_THREADS = T1_SM_WARPS * 32;              // 256
+constexpr int T1_THREADS = T1_SM_THREADS + 64;
+constexpr int T1_OFF_Q = 0, T1_OFF_K = 128 * 128, T1_OFF_V = T1_OFF_K + TILE_BYTES;
+constexpr int T1_OFF_P3 = T1_OFF_V + TILE_BYTES;             // 4th P block (blocks 0-2 alias Q|K)
+constexpr int T1_OFF_SMALL = T1_OFF_P3 + 16384;
+constexpr int T1_SMEM = T1_OFF_SMALL + 8192 + 1024;
+
+struct Small1 {
+  unsigned long long bar[8];
+  uint32_t tmem_base, pad_[3];
+  float q256[64], k256[64], v256[64];
+  float p256[128];
+  float s256[128];
+  float tsc[260];
+  float smax[2][128];
+  float ssum[2][128];
+};
+static_assert(sizeof(Small1) <= 8192, "Small1");
+
+template <bool FULL>
+__global__ void __launch_bounds__(T1_THREADS, 2)
+attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                    const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int C) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t sbase = raw + pad;
+  Small1* sm = reinterpret_cast<Small1*>(smem + T1_OFF_SMALL);
+  const uint32_t bar0 = sbase + T1_OFF_SMALL + (uint32_t)offsetof(Small1, bar);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  enum { B_LOAD = 0, B_S = 1, B_P = 2, B_O = 3, B_TAIL = 4 };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x & 1;                              // query tile of this CTA
+  const int h = (blockIdx.x >> 1) % H, n = (blockIdx.x >> 1) / H;
+  const long long row0 = (long long)n * S;
+  const int ld = 3 * C;
+  const bool key256 = S > 256;
+  const bool do_tail = key256 && t == 1;                     // query row 256 rides with tile 1
+
+  if (warp == T1_SM_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    mbar_init(BAR(B_LOAD), 1);
+    mbar_init(BAR(B_S), 1);
+    mbar_init(BAR(B_P), T1_SM_THREADS);
+    mbar_init(BAR(B_O), 1);
+    mbar_init(BAR(B_TAIL), T1_SM_THREADS);
+    mbar_fence_init();
+  }
+  if (warp == T1_SM_WARPS + 1) {
+    tmem_alloc(sbase + T1_OFF_SMALL + (uint32_t)offsetof(Small1, tmem_base), 256);
+    const bf16* r = qkv + (row0 + 256) * ld + h * 64;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int d = lane * 2 + j;
+      sm->q256[d] = key256 ? __bfloat162float(r[d]) : 0.f;
+      sm->k256[d] = key256 ? __bfloat162float(r[C + d]) : 0.f;
+      sm->v256[d] = key256 ? __bfloat162float(r[2 * C + d]) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  constexpr float SCALE = 0.125f;
+  constexpr float LOG2E = 1.4426950408889634f;
+  // P block kb lives at: blocks 0..2 -> the Q|K region, block 3 -> its own 16 KB
+  auto p_off = [&](int kb) { return kb < 3 ? (uint32_t)(kb * 16384) : (uint32_t)T1_OFF_P3; };
+
+  if (warp == T1_SM_WARPS) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(BAR(B_LOAD), 128 * 128 + 2 * TILE_BYTES);
+      tma_load_2d(sbase + T1_OFF_Q, &tmap_q, BAR(B_LOAD), h * 64, (int)row0 + t * 128);
+      tma_load_2d(sbase + T1_OFF_K, &tmap_kv, BAR(B_LOAD), C + h * 64, (int)row0);
+      tma_load_2d(sbase + T1_OFF_V, &tmap_kv, BAR(B_LOAD), 2 * C + h * 64, (int)row0);
+      mbar_wait(BAR(B_LOAD), 0);
+      tc_fence_after();
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);
+      const uint64_t kdesc = umma_desc_k_sw128(sbase + T1_OFF_K);
+      const uint64_t qdesc = umma_desc_k_sw128(sbase + T1_OFF_Q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(tmem, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+      tc_commit(BAR(B_S));
+      mbar_wait(BAR(B_P), 0);
+      tc_fence_after();
+      const uint64_t vdesc = umma_desc_mn_sw128(sbase + T1_OFF_V);
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        const uint64_t pdesc = umma_desc_k_sw128(sbase + p_off(kk >> 2)) + 2u * (kk & 3);
+        tc_mma_bf16(tmem, pdesc, vdesc + (uint64_t)((kk * 2048) >> 4), idesc_o, kk != 0 ? 1u : 0u);
+      }
+      tc_commit(BAR(B_O));
+    }
+  } else if (warp == T1_SM_WARPS + 1) {
+    if (do_tail) {
+      mbar_wait(BAR(B_TAIL), 0);
+      if (lane == 0) {
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) d += sm->q256[c] * sm->k256[c];
+        sm->tsc[256] = bf16r(d) * SCALE;
+      }
+      __syncwarp();
+      float sc[9];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int j = lane + 32 * i;
+        sc[i] = (j <= 256) ? sm->tsc[j] : -INFINITY;
+        mx = fmaxf(mx, sc[i]);
+      }
+      mx = warp_max(mx);
+      float sum = 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int j = lane + 32 * i;
+        const float p = (j <= 256) ? ex2_approx((sc[i] - mx) * LOG2E) : 0.f;
+        sum += p;
+        if (j <= 256) sm->tsc[j] = bf16r(p);
+      }
+      sum = warp_sum(sum);
+      __syncwarp();
+      float o0 = 0.f, o1 = 0.f;
+      const int ch = lane >> 2, wi = (lane & 3) * 4;
+#pragma unroll 8
+      for (int j = 0; j < 256; ++j) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(smem + T1_OFF_V + sw128(j, ch) + wi);
+        const float p = sm->tsc[j];
+        o0 += p * bf16lo(v);
+        o1 += p * bf16hi(v);
+      }
+      o0 += sm->tsc[256] * sm->v256[2 * lane];
+      o1 += sm->tsc[256] * sm->v256[2 * lane + 1];
+      const float inv = 1.0f / sum;
+      *reinterpret_cast<uint32_t*>(out + (row0 + 256) * C + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+    }
+  } else {
+    const int q4 = warp & 3, hf = warp >> 2;                  // TMEM lane quarter, column half
+    const int r = q4 * 32 + lane;
+    mbar_wait(BAR(B_LOAD), 0);
+    if (key256) {
+      const int tix = threadIdx.x;                            // 0..255
+      if (tix < 128) sm->s256[tix] = bf16r(dot64(smem + T1_OFF_Q, tix, sm->k256)) * SCALE;
+      if (do_tail) sm->tsc[tix] = bf16r(dot64(smem + T1_OFF_K, tix, sm->q256)) * SCALE;
+    } else if (threadIdx.x < 128) {
+      sm->s256[threadIdx.x] = -INFINITY;
+    }
+    mbar_arrive(BAR(B_TAIL));
+    const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + hf * 128;
+    const int n_valid = FULL ? 128 : max(0, min(128, S - hf * 128));
+    mbar_wait(BAR(B_S), 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_32x32(taddr + c * 32, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (FULL || c * 32 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    sm->smax[hf][r] = bf16r(mx) * SCALE;
+    named_bar_sync(1, T1_SM_THREADS);                         // also: all Q / K row reads are done
+    const float m = fmaxf(fmaxf(sm->smax[0][r], sm->smax[1][r]), sm->s256[r]);
+    const float mb = m * LOG2E;
+    if (hf == 0) sm->p256[r] = key256 ? ex2_approx(sm->s256[r] * LOG2E - mb) : 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_32x32(taddr + c * 32, v);
+      tc_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t s2 = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        float p0 = ex2_approx(fmaf(bf16lo(s2), SCALE * LOG2E, -mb));
+        float p1 = ex2_approx(fmaf(bf16hi(s2), SCALE * LOG2E, -mb));
+        if (!FULL) {
+          if (c * 32 + 2 * j >= n_valid) p0 = 0.f;
+          if (c * 32 + 2 * j + 1 >= n_valid) p1 = 0.f;
+        }
+        sum += p0 + p1;
+        pk[j] = pack_bf16x2(p0, p1);
+      }
+      const int key0 = hf * 128 + c * 32;
+      const uint32_t pb = p_off(key0 >> 6);
+      const int ch0 = (key0 & 63) >> 3;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(smem + pb + sw128(r, ch0 + q)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+    sm->ssum[hf][r] = sum;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    mbar_arrive(BAR(B_P));
+    // epilogue: 32 of the 64 output columns per thread
+    mbar_wait(BAR(B_O), 0);
+    tc_fence_after();
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_32x32(tmem + ((uint32_t)(q4 * 32) << 16) + hf * 32, v);
+    tc_wait_ld();
+    const int qr = t * 128 + r;
+    if (qr < S && qr < 256) {
+      const float p256 = sm->p256[r];
+      const float total = sm->ssum[0][r] + sm->ssum[1][r] + p256;
+      const float inv = 1.0f / total;
+      const float pb = bf16r(p256);
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = __uint_as_float(v[2 * j]) + pb * sm->v256[hf * 32 + 2 * j];
+        const float b = __uint_as_float(v[2 * j + 1]) + pb * sm->v256[hf * 32 + 2 * j + 1];
+        o[j] = pack_bf16x2(a * inv, b * inv);
+      }
+      bf16* dst = out + (row0 + qr) * C + h * 64 + hf * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == T1_SM_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 }  // namespace
 
 int init_attention_tc_kernels() {
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
+  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
   return 0;
 }
 
@@ -361,6 +612,18 @@ int launch_attention_vit_tc(const bf16* qkv, bf16* out, int n_frames, int S, int
   VCL_REQUIRE(S >= 129 && S <= 257, "attention_tc: S=%d outside 129..257 (other sizes use the mma.sync kernel)", S);
   CUtensorMap tm;
   if (make_tmap_2d(&tm, qkv, (long long)n_frames * S, 3LL * C, 3LL * C, 256) != 0) return -2;
+  static const bool two_tile = getenv("VCL_ATTN_TWO_TILE") != nullptr;   // A/B: older one-CTA-per-head kernel
+  if (!two_tile) {
+    CUtensorMap tq;
+    if (make_tmap_2d(&tq, qkv, (long long)n_frames * S, 3LL * C, 3LL * C, 128) != 0) return -2;
+    if (S >= 256)
+      attn_vit_tc1_kernel<true><<<n_frames * H * 2, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C);
+    else
+      attn_vit_tc1_kernel<false><<<n_frames * H * 2, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C);
+    VCL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+  }
   if (S >= 256)
     attn_vit_tc_kernel<true><<<n_frames * H, ATC_THREADS, ATC_SMEM, stream>>>(tm, qkv, out, S, H, C);
   else
