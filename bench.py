@@ -349,7 +349,11 @@ def run_vcl(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": dec_gbs, "peak": hbm, "unit": "GB/s", "frac": dec_gbs / hbm,
-                     "traffic": None, "peak_source": src,
+                     # ncu --set full (profiles/r01_ncu_full_gemv_r1.csv, r01_ncu_full_mega_r1.csv): DRAM bytes of
+                     # the decode kernels = their algorithmic bytes (+1.9 % for the whole step, 7B, B=1)
+                     "traffic": (dec_bytes * 1.019 if (args.model == "7b" and B == 1) else None),
+                     "traffic_note": "dram__bytes_read+write per decode loop, ncu capture of one step x steps",
+                     "peak_source": src,
                      "kernel": f"decode loop: {N_NEW - 1} steps x (5 fused GEMV/attention launches x {m['layers']} layers + head), "
                                "one CUDA graph; bytes = weights streamed + KV read"},
         "stages": {"clip_ms": stage[0], "prefill_ms": stage[1], "decode_ms": stage[2],

@@ -33,7 +33,10 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 namespace vcl {
 
@@ -43,7 +46,7 @@ constexpr int MG_CWARPS = 16;
 constexpr int MG_CONSUMERS = MG_CWARPS * 32;       // 512
 constexpr int MG_THREADS = MG_CONSUMERS + 32;      // + producer warp
 constexpr int MG_KC = 1024;                        // k elements per slot
-constexpr int MG_ROWB = MG_KC * 2 + 16;            // padded row pitch inside a slot (bank spread)
+constexpr int MG_ROWB = MG_KC * 2 + 64;            // padded row pitch inside a slot (bank spread)
 constexpr int MG_SLOT_BYTES = 16 * MG_ROWB;        // 33024
 constexpr int MG_NSLOT = 5;
 constexpr int MG_RMAX = 240;                       // max rows of one phase owned by a CTA (x16)
@@ -80,10 +83,10 @@ __device__ __forceinline__ float ld_cg_bf16(const bf16* p) {
   asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
   return __uint_as_float((uint32_t)v << 16);
 }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void cbar(int id) {      // barrier among the 512 consumer threads
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(MG_CONSUMERS) : "memory");
@@ -125,38 +128,78 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
   int slot = 0;
   uint32_t par = 0;
   auto advance = [&]() { if (++slot == MG_NSLOT) { slot = 0; par ^= 1u; } };
+  // optional timeline: 8 timestamps per (CTA, phase); phases per layer: qkv, attA, attB, o, gu, down
+  const int n_phase = L * 6 + 1;
+  auto trace = [&](int phase, int ev) {
+    if (p.trace != nullptr) p.trace[((size_t)blockIdx.x * n_phase + phase) * 8 + ev] = globaltimer_ns();
+  };
 
   if (warp == MG_CWARPS) {
     // =============================== producer ===============================
-    auto stream = [&](const bf16* W, int N, int K, bool qkv) {
-      const int R = rows_per_cta(N);
-      const int r0 = blockIdx.x * R, r1 = min(N, r0 + R);
-      const int nkc = (K + MG_KC - 1) / MG_KC;
-      for (int g0 = r0; g0 < r1; g0 += 16) {
-        const int nr = min(16, r1 - g0);
-        for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t seg = (uint32_t)min(MG_KC, K - kc * MG_KC) * 2u;
-          mbar_wait(empty_bar(slot), par ^ 1u);
-          const uint32_t dst = ring0 + slot * MG_SLOT_BYTES;
-          if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), nr * seg);
-          __syncwarp();
-          if (lane < nr) {
-            const long long row = qkv ? qkv_row(g0 + lane) : (long long)(g0 + lane);
-            bulk_g2s(dst + lane * MG_ROWB, W + row * K + (long long)kc * MG_KC, seg, full_bar(slot));
-          }
-          __syncwarp();
-          advance();
+    // The fill sequence (matrix, 16-row group, k chunk) is walked by two cursors: `ld` feeds the ring,
+    // `pf` runs p.l2_slots fills ahead of it and only issues L2 prefetches (fire and forget, no
+    // shared memory), so that HBM keeps streaming while the ring is full, i.e. while the consumers sit
+    // in a grid barrier or in the attention phases.
+    struct Cursor { int m, g0, kc, r1, nkc, K; const bf16* W; bool qkv, done; };
+    auto open = [&](Cursor& c, int m) {
+      for (; m <= 4 * L; ++m) {
+        int N;
+        if (m == 4 * L) { c.W = p.lm_head; N = V; c.K = D; c.qkv = false; }
+        else {
+          const MegaLayer w = p.layers[m >> 2];
+          const int which = m & 3;
+          c.W = which == 0 ? w.wqkv : which == 1 ? w.wo : which == 2 ? w.wgu : w.wd;
+          N = which == 0 ? 3 * D : which == 1 ? D : which == 2 ? 2 * F : D;
+          c.K = which == 3 ? F : D;
+          c.qkv = which == 0;
         }
+        const int R = rows_per_cta(N);
+        const int r0 = blockIdx.x * R;
+        c.r1 = min(N, r0 + R);
+        if (r0 < c.r1) { c.m = m; c.g0 = r0; c.kc = 0; c.nkc = (c.K + MG_KC - 1) / MG_KC; return; }
+      }
+      c.done = true;
+    };
+    auto step = [&](Cursor& c) {
+      if (++c.kc == c.nkc) {
+        c.kc = 0; c.g0 += 16;
+        if (c.g0 >= c.r1) open(c, c.m + 1);
       }
     };
-    for (int l = 0; l < L; ++l) {
-      const MegaLayer w = p.layers[l];
-      stream(w.wqkv, 3 * D, D, true);
-      stream(w.wo, D, D, false);
-      stream(w.wgu, 2 * F, D, false);
-      stream(w.wd, D, F, false);
+    auto src_of = [&](const Cursor& c) {
+      const long long row = c.qkv ? qkv_row(c.g0 + lane) : (long long)(c.g0 + lane);
+      return c.W + row * c.K + (long long)c.kc * MG_KC;
+    };
+    Cursor ld, pf;
+    ld.done = false; open(ld, 0);
+    pf = ld;
+    for (int i = 0; i < MG_NSLOT && !pf.done; ++i) step(pf);          // the ring itself covers these
+    auto prefetch_one = [&]() {
+      if (pf.done) return;
+      const uint32_t seg = (uint32_t)min(MG_KC, pf.K - pf.kc * MG_KC) * 2u;
+      if (lane < min(16, pf.r1 - pf.g0))
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_of(pf)), "r"(seg) : "memory");
+      step(pf);
+    };
+    for (int i = 0; i < p.l2_slots; ++i) prefetch_one();
+    while (!ld.done) {
+      if (p.l2_slots > 0) prefetch_one();
+      const int nr = min(16, ld.r1 - ld.g0);
+      const uint32_t seg = (uint32_t)min(MG_KC, ld.K - ld.kc * MG_KC) * 2u;
+      mbar_wait(empty_bar(slot), par ^ 1u);
+      const uint32_t dst = ring0 + slot * MG_SLOT_BYTES;
+      if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), nr * seg);
+      __syncwarp();
+      if (lane < nr) bulk_g2s(dst + lane * MG_ROWB, src_of(ld), seg, full_bar(slot));
+      __syncwarp();
+      advance();
+      const int m_done = ld.m;
+      step(ld);
+      if (lane == 0 && (ld.done || ld.m != m_done)) {
+        const int l = m_done >> 2, which = m_done & 3;
+        trace(m_done == 4 * L ? L * 6 : l * 6 + (which == 0 ? 0 : which + 2), 5);
+      }
     }
-    stream(p.lm_head, V, D, false);
     return;
   }
 
@@ -174,11 +217,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
     cbar(2);
     if (tid == 0) {
       ++epoch;
+      __threadfence();                               // publish this CTA's phase output (cumulative)
       unsigned old;
-      asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(grp_cnt) : "memory");
-      if (old + 1 == group_size * epoch)
-        asm volatile("red.add.release.gpu.global.u32 [%0], 1;" ::"l"(top_cnt) : "memory");
-      while (ld_acquire_u32(top_cnt) < n_groups * epoch) {}
+      asm volatile("atom.add.relaxed.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(grp_cnt) : "memory");
+      if (old + 1 == group_size * epoch) {
+        __threadfence();
+        asm volatile("red.add.relaxed.gpu.global.u32 [%0], 1;" ::"l"(top_cnt) : "memory");
+      }
+      unsigned seen;
+      do {                                           // plain polling, ONE fence after the loop
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(top_cnt) : "memory");
+      } while (seen < n_groups * epoch);
+      __threadfence();
     }
     cbar(2);
   };
@@ -186,7 +236,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
   const int g = lane >> 2, q = lane & 3;
 
   // ---- one GEMV phase. XL(c) returns the 8 bf16 (packed) of chunk c of the input vector ----
-  auto gemv = [&](int mode, int N, int K, const bf16* norm_w, auto XL, int l) {
+  auto gemv = [&](int mode, int N, int K, const bf16* norm_w, auto XL, int l, int phase) {
+    if (tid == 0) trace(phase, 0);
     const int nch = K >> 3;
     const int R = rows_per_cta(N);
     const int r0 = blockIdx.x * R, r1 = min(N, r0 + R);
@@ -223,6 +274,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
       }
       cbar(3);
     }
+    if (tid == 0) trace(phase, 1);
     // stream the 16-row groups of this CTA out of the ring; warp w owns K blocks w, w+16 of a slot
     for (int g0 = 0; g0 < n_rows; g0 += 16) {
       float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -252,6 +304,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         part[warp * MG_RMAX + g0 + g + 8] = c[2];
       }
     }
+    if (tid == 0) trace(phase, 2);
     cbar(3);
     // epilogue
     const bool pairs = (mode == MODE_SWIGLU || mode == MODE_QKV);
@@ -298,6 +351,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         }
       }
     }
+    if (tid == 0) trace(phase, 3);
   };
 
   const int kv_len = p.pos + 1;
@@ -318,8 +372,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
 
   for (int l = 0; l < L; ++l) {
     const MegaLayer w = p.layers[l];
-    gemv(MODE_QKV, 3 * D, D, w.ln1, x_from(p.h), l);
+    gemv(MODE_QKV, 3 * D, D, w.ln1, x_from(p.h), l, l * 6);
     grid_sync();
+    if (tid == 0) { trace(l * 6, 4); trace(l * 6 + 1, 0); }
     // ---------------- attention A: scores + local statistics ----------------
     const bf16* kc_l = p.kcache + (long long)l * p.cache_layer_elems;
     const bf16* vc_l = p.vcache + (long long)l * p.cache_layer_elems;
@@ -367,7 +422,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         }
       }
     }
+    if (tid == 0) trace(l * 6 + 1, 3);
     grid_sync();
+    if (tid == 0) { trace(l * 6 + 1, 4); trace(l * 6 + 2, 0); }
     // ---------------- attention B: probabilities (global max / sum) x V ----------------
     {
       int k = 0;
@@ -420,7 +477,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
         }
       }
     }
+    if (tid == 0) trace(l * 6 + 2, 3);
     grid_sync();
+    if (tid == 0) trace(l * 6 + 2, 4);
     // ---------------- o_proj: input = bf16(sum of the 4 partial attention outputs) ----------------
     auto x_att = [&](int c) {
       const int head = c >> 4, d0 = (c & 15) * 8;
@@ -434,15 +493,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
       }
       return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     };
-    gemv(MODE_RES, D, D, nullptr, x_att, l);
+    gemv(MODE_RES, D, D, nullptr, x_att, l, l * 6 + 3);
     grid_sync();
-    gemv(MODE_SWIGLU, 2 * F, D, w.ln2, x_from(p.h), l);
+    if (tid == 0) trace(l * 6 + 3, 4);
+    gemv(MODE_SWIGLU, 2 * F, D, w.ln2, x_from(p.h), l, l * 6 + 4);
     grid_sync();
-    gemv(MODE_RES, D, F, nullptr, x_from(p.act), l);
+    if (tid == 0) trace(l * 6 + 4, 4);
+    gemv(MODE_RES, D, F, nullptr, x_from(p.act), l, l * 6 + 5);
     grid_sync();
+    if (tid == 0) trace(l * 6 + 5, 4);
   }
-  gemv(MODE_LOGITS, V, D, p.norm_w, x_from(p.h), 0);
+  gemv(MODE_LOGITS, V, D, p.norm_w, x_from(p.h), 0, L * 6);
   grid_sync();
+  if (tid == 0) trace(L * 6, 4);
   // ---- arg-max (lowest index wins ties) ----
   if (blockIdx.x == 0) {
     float best = -INFINITY;
@@ -499,8 +562,31 @@ int launch_decode_mega(const MegaParams& p, int B, cudaStream_t stream) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel, p));
+  // VCL_MEGA_TRACE=<file>: record per-CTA phase timestamps of this step and dump them (debug aid,
+  // eager launches only; layout [grid][L*6+1][8] uint64 nanoseconds)
+  static unsigned long long* trace_buf = nullptr;
+  const char* trace_path = getenv("VCL_MEGA_TRACE");
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  VCL_CUDA_OK(cudaStreamIsCapturing(stream, &cap));
+  const bool tracing = trace_path != nullptr && cap == cudaStreamCaptureStatusNone;
+  const size_t trace_n = (size_t)device_num_sms() * (p.L * 6 + 1) * 8;
+  MegaParams q = p;
+  static const int l2_slots = getenv("VCL_MEGA_L2_SLOTS") ? atoi(getenv("VCL_MEGA_L2_SLOTS")) : 12;
+  q.l2_slots = l2_slots;
+  if (tracing) {
+    if (trace_buf == nullptr) VCL_CUDA_OK(cudaMalloc(&trace_buf, trace_n * sizeof(unsigned long long)));
+    VCL_CUDA_OK(cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(unsigned long long), stream));
+    q.trace = trace_buf;
+  }
+  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_mega_kernel, q));
   count_launches(1);
+  if (tracing) {
+    std::vector<unsigned long long> host(trace_n);
+    VCL_CUDA_OK(cudaStreamSynchronize(stream));
+    VCL_CUDA_OK(cudaMemcpy(host.data(), trace_buf, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "wb");
+    if (f != nullptr) { fwrite(host.data(), sizeof(unsigned long long), trace_n, f); fclose(f); }
+  }
   return 0;
 }
 

@@ -1,0 +1,473 @@
+// Single-clip decode projections (B = 1): out[n] = x . W[n, :], one kernel per weight matrix.
+//
+// What bounds these kernels is how much of the time HBM is kept streaming. Measured on this part
+// (profiles/r01_hbm_read_probe.txt, r01_hbm_chain_probe.txt, r01_tc_trace.txt):
+//   * one B200 reads at 7.2-7.3 TB/s; a chain of 129 pure-read kernels over the step's 13.2 GB
+//     reaches 6.9-7.0 TB/s with programmatic dependent launch (the next kernel's first loads are
+//     in flight while the current one drains), 6.1-6.2 TB/s when every kernel starts cold;
+//   * cp.async.bulk rings stream as fast as the best register pipelines, cost no registers and no
+//     issue slots in the consumer warps, but the copy engine retires only ~23 copies/us per SM
+//     whatever their size: one copy per 1 KB row segment gives 3.4 TB/s, 2 KB 6.8 TB/s, so the
+//     slots have to be contiguous in memory and fetched with ONE copy each;
+//   * the CUDA-core GEMV (gemv.cu) spends ~50 instructions per KB of weights (unpack, FMA, warp
+//     shuffle reduction) and loses 10 % when a few more are added; mma.sync does the K reduction
+//     in the tensor pipe at ~6 instructions per KB;
+//   * the serial latency after griddepcontrol.wait (activation fetch + norm) is dead time for HBM
+//     once the ring is full: it is one L2 round trip here (1.0-1.4 us, was 2.9 us).
+//
+// Structure (one CTA per SM, 9 warps, 8 x 16 KB ring):
+//   warp 8      producer: walks this CTA's 16-row groups, K chunk by K chunk (512 k), and fills
+//               the ring with one bulk copy per slot. The kernel reads a decode-only copy of the
+//               matrix that the weight loader lays out slot by slot (gemv_tc_repack below):
+//               [16-row group][K chunk][32-wide K block][row half][lane] x 16 bytes, i.e. already
+//               in mma.sync A-fragment order. Weights never depend on the previous kernel, so
+//               the producer starts immediately, BEFORE the dependency wait.
+//   warps 0-7   consumers: griddepcontrol.wait, stage the activation vector in shared memory (bf16,
+//               optionally RMS-normalised), then per slot two m16n8k16 MMAs per 32-wide K block:
+//               A fragments with two conflict-free LDS.128 (lane l reads bytes [16 l, 16 l + 16)
+//               of each 512-byte row half), column 0 of the B fragment from the activation
+//               vector. fp32 accumulators live across the K chunks of a row group; the 8 per-warp
+//               partials meet in shared memory after every group and the fused epilogues (RoPE +
+//               KV append, SwiGLU, residual, logits) run once at the end.
+// Ring depth: 6 slots -> 79 ms per 31 decode steps (7B), 8 -> 74 ms, 9 -> 79 ms, 13 -> 81 ms; two
+// half-SM CTAs of consecutive kernels (6 slots each) -> 77-82 ms. 8 it is.
+//
+// Arithmetic and rounding points are those of gemv.cu (reference: transformers/models/llama/
+// modeling_llama.py:53-67 RMSNorm, :124-168 RoPE, :171-184 MLP, :325,331 residuals).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+namespace vcl {
+
+namespace {
+
+enum { MODE_RES = 0, MODE_SWIGLU = 1, MODE_QKV = 2, MODE_LOGITS = 3 };
+constexpr int TC_CWARPS = 8;
+constexpr int TC_CONSUMERS = TC_CWARPS * 32;
+constexpr int TC_THREADS = TC_CONSUMERS + 32;
+constexpr int TC_KC = 512;                          // k elements per slot
+constexpr int TC_SLOT_BYTES = 16 * TC_KC * 2;       // 16 KB, one bulk copy
+constexpr int TC_MAX_SLOTS = 8;                     // measured optimum (7 B shapes): 6 -> 79 ms, 8 -> 74 ms, 9 -> 79 ms per 31 steps
+constexpr int TC_SMEM_BUDGET = 160 * 1024;          // one CTA per SM; the rest of the SM stays free for the
+                                                    // attention kernel's CTAs, which launch early (PDL)
+
+struct TcParams {
+  const bf16* x;
+  const bf16* W;                    // tiled copy (gemv_tc_repack)
+  int N, K;
+  int n_slots;
+  const bf16* norm_w; float eps;
+  bf16* out;                        // RES: [N]; SWIGLU: [N/2]
+  const bf16* res;
+  bf16* q_out; bf16* kcache; bf16* vcache;
+  const bf16* cos_t; const bf16* sin_t;
+  int H, s_max, pos;
+  float* logits;
+  unsigned long long* trace;        // optional [grid][8] timestamps (VCL_TC_TRACE), else nullptr
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint4 ld_cg_v4(const void* p) {     // served by L2: never a stale L1 line
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void cbar() {            // barrier among the consumer warps only
+  asm volatile("bar.sync 1, %0;" ::"r"(TC_CONSUMERS) : "memory");
+}
+__device__ __forceinline__ void tc_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                       uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// virtual row -> weight row. QKV: the rows of a RoPE pair (d, d+64) are made adjacent (2p, 2p+1)
+template <int MODE>
+__device__ __forceinline__ long long map_row(int v) {
+  if (MODE == MODE_QKV) return (long long)(v >> 7) * 128 + ((v & 127) >> 1) + (((v & 127) & 1) << 6);
+  return v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: ring[n_slots] | x[K] bf16 | pbuf[2][TC_CWARPS][16] | result[r_cap] fp32 | red | barriers
+  const int K = p.K, N = p.N;
+  const int n_slots = p.n_slots;
+  const int n_groups = (N + 15) >> 4;
+  const int nkc = (K + TC_KC - 1) / TC_KC;
+  // contiguous blocks of 16-row groups per CTA, sizes differing by at most one group. (Cutting the
+  // matrix into equal SLOT shares with partial sums exchanged between neighbours - stream-K - was
+  // measured: every CTA then streams the same bytes, but the kernels got 9 % slower; per-SM
+  // throughput is latency-bound, not bandwidth-shared, so the early finishers were not the problem.)
+  const int grp_begin = (int)(((long long)blockIdx.x * n_groups) / gridDim.x);
+  const int grp_end = (int)(((long long)(blockIdx.x + 1) * n_groups) / gridDim.x);
+  const int my_groups = grp_end - grp_begin;
+  const int R = my_groups * 16;                      // local rows (the last group may be partial)
+  const int row0 = grp_begin * 16;
+
+  bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_slots * TC_SLOT_BYTES);
+  float* pbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)K * 2);
+  float* result = pbuf + 2 * TC_CWARPS * 16;
+  const int r_cap = ((n_groups + gridDim.x - 1) / gridDim.x) * 16;     // same on every CTA (layout)
+  float* red = result + r_cap;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16);
+  const uint32_t ring0 = smem_u32(smem);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TC_MAX_SLOTS + s); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto trace = [&](int ev) { if (p.trace != nullptr) p.trace[blockIdx.x * 8 + ev] = globaltimer_ns(); };
+  if (tid == 0) {
+    trace(0);
+    for (int s = 0; s < n_slots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), TC_CWARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();                           // the next kernel may take the other half of the SM
+
+  int slot = 0;
+  uint32_t par = 0;
+  auto advance = [&]() { if (++slot == n_slots) { slot = 0; par ^= 1u; } };
+
+  if (warp == TC_CWARPS) {
+    // =============================== producer ===============================
+    if (lane == 0) {
+      trace(5);
+      for (int g = 0; g < my_groups; ++g) {
+        const bf16* src = p.W + (size_t)(grp_begin + g) * 16 * K;
+        for (int kc = 0; kc < nkc; ++kc) {
+          const uint32_t bytes = (uint32_t)min(TC_KC, K - kc * TC_KC) * 32u;      // 16 rows x 2 B
+          mbar_wait(empty_bar(slot), par ^ 1u);
+          mbar_arrive_expect_tx(full_bar(slot), bytes);
+          bulk_g2s(ring0 + slot * TC_SLOT_BYTES, src + (size_t)kc * TC_KC * 16, bytes, full_bar(slot));
+          advance();
+        }
+      }
+      trace(6);
+    }
+    return;
+  }
+
+  // =============================== consumers ===============================
+  // Activation vector -> shared memory (bf16), RMS-normalised when the layer norm is fused. The
+  // dependent latency after the wait is ONE L2 round trip: the norm weights (constants) are
+  // parked in the x buffer before the wait, and every thread issues all its x loads back to back.
+  constexpr int XU = 7;                               // 16-byte chunks per thread: K <= 14336
+  const int nch = K >> 3;
+  if (p.norm_w != nullptr) {
+#pragma unroll
+    for (int i = 0; i < XU; ++i) {
+      const int c = tid + i * TC_CONSUMERS;
+      if (c < nch) *reinterpret_cast<uint4*>(xs + c * 8) = __ldg(reinterpret_cast<const uint4*>(p.norm_w + c * 8));
+    }
+  }
+  pdl_wait();                                        // the activation vector comes from the previous kernel
+  if (tid == 0) trace(1);
+  {
+    uint4 xv[XU];
+#pragma unroll
+    for (int i = 0; i < XU; ++i) {
+      const int c = tid + i * TC_CONSUMERS;
+      xv[i] = (c < nch) ? ld_cg_v4(p.x + c * 8) : make_uint4(0, 0, 0, 0);
+    }
+    if (p.norm_w != nullptr) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < XU; ++i) {
+        const uint4 u = xv[i];
+        const float f0 = bf16lo(u.x), f1 = bf16hi(u.x), f2 = bf16lo(u.y), f3 = bf16hi(u.y);
+        const float f4 = bf16lo(u.z), f5 = bf16hi(u.z), f6 = bf16lo(u.w), f7 = bf16hi(u.w);
+        ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) red[warp] = ss;
+      cbar();
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
+      const float rstd = rsqrtf(tot / (float)K + p.eps);
+#pragma unroll
+      for (int i = 0; i < XU; ++i) {
+        const int c = tid + i * TC_CONSUMERS;
+        if (c < nch) {
+          const uint4 u = xv[i];
+          const uint4 gw = *reinterpret_cast<const uint4*>(xs + c * 8);
+          uint4 o;
+          // w * bf16(x * rstd), the product rounded to bf16 again (LlamaRMSNorm)
+          o.x = bf16x2_mul(gw.x, pack_bf16x2(bf16lo(u.x) * rstd, bf16hi(u.x) * rstd));
+          o.y = bf16x2_mul(gw.y, pack_bf16x2(bf16lo(u.y) * rstd, bf16hi(u.y) * rstd));
+          o.z = bf16x2_mul(gw.z, pack_bf16x2(bf16lo(u.z) * rstd, bf16hi(u.z) * rstd));
+          o.w = bf16x2_mul(gw.w, pack_bf16x2(bf16lo(u.w) * rstd, bf16hi(u.w) * rstd));
+          *reinterpret_cast<uint4*>(xs + c * 8) = o;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < XU; ++i) {
+        const int c = tid + i * TC_CONSUMERS;
+        if (c < nch) *reinterpret_cast<uint4*>(xs + c * 8) = xv[i];
+      }
+    }
+    cbar();
+  }
+  if (tid == 0) trace(2);
+
+  const int g = lane >> 2, q = lane & 3;
+  for (int grp = 0; grp < my_groups; ++grp) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int kb_n = min(TC_KC, K - kc * TC_KC) >> 5;          // 32-wide K blocks in this slot
+      mbar_wait(full_bar(slot), par);
+      const uint8_t* base = smem + slot * TC_SLOT_BYTES;
+#pragma unroll
+      for (int t = 0; t < TC_KC / 32 / TC_CWARPS; ++t) {
+        const int kb = warp + TC_CWARPS * t;
+        if (kb < kb_n) {
+          const uint4 wa = *reinterpret_cast<const uint4*>(base + kb * 1024 + lane * 16);        // row g
+          const uint4 wb = *reinterpret_cast<const uint4*>(base + kb * 1024 + 512 + lane * 16);  // row g+8
+          uint4 xq = make_uint4(0, 0, 0, 0);
+          if (g == 0) xq = *reinterpret_cast<const uint4*>(xs + kc * TC_KC + kb * 32 + q * 8);
+          tc_mma(c, wa.x, wb.x, wa.y, wb.y, xq.x, xq.y);
+          tc_mma(c, wa.z, wb.z, wa.w, wb.w, xq.z, xq.w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(slot));
+      advance();
+    }
+    // the 8 per-warp partials of this row group meet in shared memory (double-buffered: the barrier of
+    // the next group orders the reads below before the buffer is written again)
+    float* pb = pbuf + (grp & 1) * TC_CWARPS * 16;
+    if (q == 0) {                                     // column 0: rows g (c[0]) and g+8 (c[2])
+      pb[warp * 16 + g] = c[0];
+      pb[warp * 16 + g + 8] = c[2];
+    }
+    cbar();
+    if (tid < 16) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < TC_CWARPS; ++w) v += pb[w * 16 + tid];
+      result[grp * 16 + tid] = v;
+    }
+  }
+  cbar();
+  if (tid == 0) trace(3);
+
+  // ---------------- epilogue: combine the 8 warp partials ----------------
+  constexpr bool PAIRS = (MODE == MODE_SWIGLU || MODE == MODE_QKV);
+  const int n_items = PAIRS ? R / 2 : R;
+  for (int it = tid; it < n_items; it += TC_CONSUMERS) {
+    const int rr = PAIRS ? 2 * it : it;
+    const int vrow = row0 + rr;
+    if (vrow >= N) continue;
+    const float v0 = result[rr];
+    const float v1 = PAIRS ? result[rr + 1] : 0.f;
+    if (MODE == MODE_RES) {
+      float y = bf16r(v0);
+      if (p.res != nullptr) y += __bfloat162float(p.res[vrow]);
+      p.out[vrow] = __float2bfloat16_rn(y);
+    } else if (MODE == MODE_LOGITS) {
+      p.logits[vrow] = bf16r(v0);
+    } else if (MODE == MODE_SWIGLU) {
+      const float gt = bf16r(v0);
+      const float sg = bf16r(__fdividef(gt, 1.0f + __expf(-gt)));
+      p.out[vrow >> 1] = __float2bfloat16_rn(sg * bf16r(v1));
+    } else {  // MODE_QKV: vrow = (which*H + head)*128 + 2*d
+      const int hr = vrow >> 7;
+      const int which = hr / p.H, head = hr - which * p.H;
+      const int d = (vrow & 127) >> 1;
+      const float lo = bf16r(v0), hi = bf16r(v1);
+      const long long coff = ((long long)head * p.s_max + p.pos) * 128;
+      if (which == 2) {
+        p.vcache[coff + d] = __float2bfloat16_rn(lo);
+        p.vcache[coff + d + 64] = __float2bfloat16_rn(hi);
+      } else {
+        const float cs = __bfloat162float(p.cos_t[(long long)p.pos * 64 + d]);
+        const float sn = __bfloat162float(p.sin_t[(long long)p.pos * 64 + d]);
+        const float olo = bf16r(lo * cs) + bf16r(-hi * sn);
+        const float ohi = bf16r(hi * cs) + bf16r(lo * sn);
+        if (which == 0) {
+          p.q_out[head * 128 + d] = __float2bfloat16_rn(olo);
+          p.q_out[head * 128 + d + 64] = __float2bfloat16_rn(ohi);
+        } else {
+          p.kcache[coff + d] = __float2bfloat16_rn(olo);
+          p.kcache[coff + d + 64] = __float2bfloat16_rn(ohi);
+        }
+      }
+    }
+  }
+  if (tid == 0) { trace(4); if (p.trace != nullptr) p.trace[blockIdx.x * 8 + 7] = ((unsigned long long)MODE << 32) | (unsigned)N; }
+}
+
+// row-major W[N][K] -> tiled copy. One thread per 16-byte chunk of the output.
+__global__ void gemv_tc_repack_kernel(const bf16* __restrict__ W, bf16* __restrict__ dst, int N, int K, int qkv) {
+  const size_t chunks_per_group = (size_t)2 * K;                      // 16 rows x K x 2 B / 16 B
+  const size_t n_chunks = (size_t)((N + 15) >> 4) * chunks_per_group;
+  for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_chunks; o += (size_t)gridDim.x * blockDim.x) {
+    const int grp = (int)(o / chunks_per_group);
+    const size_t off = (o - (size_t)grp * chunks_per_group) * 16;     // byte offset inside the group
+    const int kc = (int)(off / ((size_t)TC_KC * 32));
+    const int within = (int)(off - (size_t)kc * TC_KC * 32);
+    const int kb = within >> 10, r = within & 1023;
+    const int half = r >> 9, l = (r & 511) >> 4;
+    const int row = grp * 16 + (l >> 2) + 8 * half;
+    const int k = kc * TC_KC + kb * 32 + (l & 3) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < N) {
+      const long long src_row = qkv ? map_row<MODE_QKV>(row) : (long long)row;
+      v = *reinterpret_cast<const uint4*>(W + src_row * K + k);
+    }
+    *reinterpret_cast<uint4*>(dst + o * 8) = v;
+  }
+}
+
+// shared-memory plan for (N, K) on `grid` CTAs; returns the slot count (0 = does not fit)
+int plan(int N, int K, int grid, size_t* smem_bytes) {
+  const int n_groups = (N + 15) / 16;
+  if (n_groups < grid) return 0;                     // every CTA streams at least one row group
+  const int r_cap = ((n_groups + grid - 1) / grid) * 16;
+  const size_t fixed = (size_t)K * 2 + (size_t)(2 * TC_CWARPS * 16 + r_cap) * 4 + 16 * 4 + 2 * TC_MAX_SLOTS * 8 + 128;
+  static const int env_slots = getenv("VCL_GEMV_TC_SLOTS") ? atoi(getenv("VCL_GEMV_TC_SLOTS")) : 0;
+  static const size_t budget = getenv("VCL_GEMV_TC_SMEM_KB") ? (size_t)atoi(getenv("VCL_GEMV_TC_SMEM_KB")) * 1024 : (size_t)TC_SMEM_BUDGET;
+  if (fixed + 2 * (size_t)TC_SLOT_BYTES > budget) return 0;
+  int slots = (int)((budget - fixed) / TC_SLOT_BYTES);
+  if (slots > TC_MAX_SLOTS) slots = TC_MAX_SLOTS;
+  if (env_slots > 0 && env_slots < slots) slots = env_slots;
+  *smem_bytes = (size_t)slots * TC_SLOT_BYTES + fixed;
+  return slots;
+}
+
+// VCL_TC_TRACE: every launch writes 8 timestamps per CTA into the next record of a device buffer;
+// vcl_debug_tc_trace_dump() (below) writes the records to a file. Debug aid for eager runs.
+constexpr int TC_TRACE_RECORDS = 1024;
+unsigned long long* g_trace = nullptr;
+int g_trace_next = 0;
+
+template <int MODE>
+int launch(TcParams p, cudaStream_t stream) {
+  const int grid = device_num_sms();
+  static const bool tracing = getenv("VCL_TC_TRACE") != nullptr;
+  if (tracing) {
+    const size_t rec = (size_t)grid * 8;
+    if (g_trace == nullptr) {
+      VCL_CUDA_OK(cudaMalloc(&g_trace, TC_TRACE_RECORDS * rec * sizeof(unsigned long long)));
+      VCL_CUDA_OK(cudaMemset(g_trace, 0, TC_TRACE_RECORDS * rec * sizeof(unsigned long long)));
+    }
+    p.trace = g_trace + (size_t)(g_trace_next % TC_TRACE_RECORDS) * rec;
+    ++g_trace_next;
+  }
+  size_t smem = 0;
+  p.n_slots = plan(p.N, p.K, grid, &smem);
+  VCL_REQUIRE(p.n_slots >= 2, "gemv_tc: N=%d K=%d does not fit the shared-memory plan", p.N, p.K);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemv_tc_kernel<MODE>, p));
+  count_launches(1);
+  return 0;
+}
+
+TcParams base(const GemvArgs& g) {
+  TcParams p = {};
+  p.x = g.x; p.W = g.W_tiled; p.N = g.N; p.K = g.K; p.norm_w = g.norm_w; p.eps = g.eps;
+  return p;
+}
+
+}  // namespace
+
+extern "C" int vcl_debug_tc_trace_dump(const char* path) {
+  if (g_trace == nullptr) return -1;
+  const size_t n = (size_t)TC_TRACE_RECORDS * device_num_sms() * 8;
+  std::vector<unsigned long long> host(n + 2);
+  VCL_CUDA_OK(cudaDeviceSynchronize());
+  VCL_CUDA_OK(cudaMemcpy(host.data() + 2, g_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  host[0] = (unsigned long long)g_trace_next; host[1] = (unsigned long long)device_num_sms();
+  FILE* f = fopen(path, "wb");
+  if (f == nullptr) return -2;
+  fwrite(host.data(), sizeof(unsigned long long), n + 2, f);
+  fclose(f);
+  return 0;
+}
+
+int init_gemv_tc_kernels() {
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel<MODE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel<MODE_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel<MODE_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel<MODE_LOGITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  return 0;
+}
+
+// B = 1, 16-byte aligned operands, K a multiple of 32 and a shared-memory plan that fits
+bool gemv_tc_supported(const GemvArgs& g) {
+  static const bool off = getenv("VCL_GEMV_LEGACY") != nullptr;
+  if (off || g.B != 1 || g.W_tiled == nullptr || g.K % 32 != 0 || g.K > 14336 || g.N < 16) return false;
+  if (((uintptr_t)g.x % 16) != 0 || ((uintptr_t)g.W_tiled % 16) != 0) return false;
+  size_t smem = 0;
+  return plan(g.N, g.K, device_num_sms(), &smem) >= 2;
+}
+
+size_t gemv_tc_tiled_elems(int N, int K) { return (size_t)((N + 15) / 16) * 16 * K; }
+
+int launch_gemv_tc_repack(const bf16* W, bf16* dst, int N, int K, bool qkv_pairs, cudaStream_t stream) {
+  VCL_REQUIRE(K % 32 == 0, "gemv_tc repack: K=%d must be a multiple of 32", K);
+  VCL_REQUIRE(!qkv_pairs || N % 128 == 0, "gemv_tc repack: q/k/v rows must come in heads of 128 (N=%d)", N);
+  gemv_tc_repack_kernel<<<device_num_sms() * 8, 256, 0, stream>>>(W, dst, N, K, qkv_pairs ? 1 : 0);
+  VCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemv_tc_residual(const GemvArgs& g, bf16* out, const bf16* res, cudaStream_t stream) {
+  TcParams p = base(g);
+  p.out = out; p.res = res;
+  return launch<MODE_RES>(p, stream);
+}
+
+int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, cudaStream_t stream) {
+  VCL_REQUIRE(g.N % 2 == 0, "gemv swiglu: N must be even (interleaved gate/up rows)");
+  TcParams p = base(g);
+  p.out = out;
+  return launch<MODE_SWIGLU>(p, stream);
+}
+
+int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, bf16* kcache, bf16* vcache, const bf16* cos_t,
+                            const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream) {
+  TcParams p = base(g);
+  p.q_out = q_out; p.kcache = kcache; p.vcache = vcache; p.cos_t = cos_t; p.sin_t = sin_t;
+  p.H = H; p.s_max = s_max; p.pos = pos;
+  return launch<MODE_QKV>(p, stream);
+}
+
+int launch_gemv_tc_logits(const GemvArgs& g, float* logits, cudaStream_t stream) {
+  TcParams p = base(g);
+  p.logits = logits;
+  return launch<MODE_LOGITS>(p, stream);
+}
+
+}  // namespace vcl

@@ -114,6 +114,8 @@ struct MegaParams {
   int* tok_out; long long tok_out_stride;
   int pos;
   unsigned int* barrier;            // grid-barrier counter (zeroed by the launcher)
+  int l2_slots;                     // fills of L2 prefetch kept ahead of the shared-memory ring
+  unsigned long long* trace;        // optional per-CTA phase timestamps (VCL_MEGA_TRACE), else nullptr
 };
 int init_decode_mega_kernels();
 bool decode_mega_supported(int B, int D, int F, int V);
@@ -123,6 +125,7 @@ int launch_decode_mega(const MegaParams& p, int B, cudaStream_t stream);
 struct GemvArgs {
   const bf16* x = nullptr; long long ldx = 0;   // [B, K]
   const bf16* W = nullptr;                      // [N, K]
+  const bf16* W_tiled = nullptr;                // optional decode-only tiled copy (gemv_tc.cu), B = 1
   int B = 0, N = 0, K = 0;
   const bf16* norm_w = nullptr; float eps = 0;  // optional fused RMSNorm prologue
 };
@@ -136,6 +139,19 @@ int launch_gemv_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kc
                          const bf16* cos_t, const bf16* sin_t, int H, int head_dim, int s_max,
                          int pos, cudaStream_t stream);
 int init_gemv_kernels();
+
+// ---- gemv_tc.cu : B = 1 variant (bulk-copy ring + mma.sync, two kernels co-resident per SM) ------
+// The launch_gemv_* entry points above route to these when gemv_tc_supported(g).
+int init_gemv_tc_kernels();
+bool gemv_tc_supported(const GemvArgs& g);
+size_t gemv_tc_tiled_elems(int N, int K);     // elements of the tiled copy of an [N, K] matrix
+// qkv_pairs: rows are taken in the order of the fused q/k/v kernel (RoPE pairs adjacent)
+int launch_gemv_tc_repack(const bf16* W, bf16* dst, int N, int K, bool qkv_pairs, cudaStream_t stream);
+int launch_gemv_tc_residual(const GemvArgs& g, bf16* out, const bf16* res, cudaStream_t stream);
+int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, cudaStream_t stream);
+int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, bf16* kcache, bf16* vcache, const bf16* cos_t,
+                            const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream);
+int launch_gemv_tc_logits(const GemvArgs& g, float* logits, cudaStream_t stream);
 // logits (bf16-rounded, stored fp32) [B, N]
 int launch_gemv_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
 
