@@ -354,8 +354,8 @@ def run_vcl(args, rank, world, local_rank):
                      "traffic": (dec_bytes * 1.019 if (args.model == "7b" and B == 1) else None),
                      "traffic_note": "dram__bytes_read+write per decode loop, ncu capture of one step x steps",
                      "peak_source": src,
-                     "kernel": f"decode loop: {N_NEW - 1} steps x (5 fused GEMV/attention launches x {m['layers']} layers + head), "
-                               "one CUDA graph; bytes = weights streamed + KV read"},
+                     "kernel": f"decode loop: {N_NEW - 1} steps x (4 weight-streaming gemv_tc launches + attention per layer x "
+                               f"{m['layers']} layers + head), one CUDA graph; bytes = weights streamed + KV read"},
         "stages": {"clip_ms": stage[0], "prefill_ms": stage[1], "decode_ms": stage[2],
                    "clip_tflops": B * w["vit_flops"] / (stage[0] * 1e-3) / 1e12,
                    "prefill_tflops": B * w["prefill_flops"] / (stage[1] * 1e-3) / 1e12,
