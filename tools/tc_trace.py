@@ -66,6 +66,22 @@ for k in range(per_step):
 for key, ds in rows.items():
     avg = {kk: float(np.mean([d[kk] for d in ds])) for kk in ds[0] if kk not in ("entry_min", "wait_done", "end")}
     print(key, " ".join("%s=%.2f" % kv for kv in avg.items()))
+apath = os.path.join(ROOT, "gpurun_out", "attn_trace.bin")
+has_attn = hasattr(lib, "vcl_debug_attn_trace_dump")   # only in builds with the attention trace hook
+if has_attn and lib.vcl_debug_attn_trace_dump(apath.encode()) == 0:
+    ar = np.fromfile(apath, dtype=np.uint64)
+    an, ac = int(ar[0]), int(ar[1])
+    at = ar[2:].reshape(-1, ac, 8).astype(np.int64)[an - L:an]          # last step: one launch per layer
+    rows_a = []
+    for l in range(1, L):
+        a = at[l]
+        qkv_end = recs[4 * l][:, 4].max(); o_wait = recs[4 * l + 1][:, 1].min()
+        rows_a.append(dict(entry_before_qkv_end=(qkv_end - a[:, 0].max()) / 1e3, qkv_end_to_wait=(a[:, 1].min() - qkv_end) / 1e3,
+                           wait_to_q=(a[:, 4] - a[:, 1]).mean() / 1e3, q_to_scores=(a[:, 5] - a[:, 4]).mean() / 1e3,
+                           scores_to_sync1=(a[:, 2] - a[:, 5]).mean() / 1e3, sync1=(a[:, 6] - a[:, 2]).mean() / 1e3,
+                           pv=(a[:, 7] - a[:, 6]).mean() / 1e3, sync2_write=(a[:, 3] - a[:, 7]).mean() / 1e3,
+                           total_after_wait=(a[:, 3].max() - a[:, 1].min()) / 1e3, end_to_o_wait=(o_wait - a[:, 3].max()) / 1e3))
+    print("attention", " ".join("%s=%.2f" % (k, float(np.mean([r[k] for r in rows_a]))) for k in rows_a[0]))
 lay = [(recs[4 * (l + 1)][:, 1].min() - recs[4 * l][:, 1].min()) / 1e3 for l in range(L - 1)]
 print("per-layer us", [round(x, 1) for x in lay])
 sys.stdout.flush()
