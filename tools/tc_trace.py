@@ -39,50 +39,38 @@ lib.vcl_debug_tc_trace_dump.argtypes = [ctypes.c_char_p]
 print("dump rc", lib.vcl_debug_tc_trace_dump(path.encode()))
 raw = np.fromfile(path, dtype=np.uint64)
 n_rec, G = int(raw[0]), int(raw[1])
-t = raw[2:].reshape(-1, G, 8).astype(np.int64)
-per_step = 4 * L + 1
+t = raw[2:].reshape(-1, G, 4, 8).astype(np.int64)
+fused = os.environ.get("VCL_DECODE_FUSED") is not None
+per_step = (L + 1) if fused else (4 * L + 1)
 recs = t[n_rec - per_step:n_rec]
 names = {2: "qkv", 0: "res", 1: "swiglu", 3: "logits"}
-mb = {("qkv", 12288): 100.7, ("res", 4096): None, ("swiglu", 22016): 180.4, ("logits", 32003): 262.2}
-t0 = recs[0][:, 0].min()
-print("step span us", (recs[-1][:, 4].max() - t0) / 1e3, "kernels", per_step)
-rows = {}
-prev_end = None
-for k in range(per_step):
-    r = recs[k]
-    mode = int(r[0, 7] >> 32); N = int(r[0, 7] & 0xffffffff)
-    key = names[mode] + ("_o" if (mode == 0 and k % 4 == 1) else "_down" if mode == 0 else "")
-    entry, waitd, xst, loop, end, p0, p1 = (r[:, i] for i in range(7))
-    d = dict(entry_min=(entry.min() - t0) / 1e3, entry_spread=(entry.max() - entry.min()) / 1e3,
-             wait_done=(waitd.min() - t0) / 1e3, wait_spread=(waitd.max() - waitd.min()) / 1e3,
-             x_stage=(xst - waitd).mean() / 1e3, stream=(loop - xst).mean() / 1e3, stream_max=(loop.max() - xst.min()) / 1e3,
-             epi=(end - loop).mean() / 1e3, total=(end.max() - waitd.min()) / 1e3,
-             prefetch_lead=(waitd - p0).mean() / 1e3, prod_done_before_end=(end - p1).mean() / 1e3,
-             gap_prev_end_to_wait=((waitd.min() - prev_end) / 1e3 if prev_end is not None else 0.0),
-             end=(end.max() - t0) / 1e3)
-    prev_end = end.max()
-    if k >= 4:
-        rows.setdefault(key, []).append(d)
-for key, ds in rows.items():
-    avg = {kk: float(np.mean([d[kk] for d in ds])) for kk in ds[0] if kk not in ("entry_min", "wait_done", "end")}
-    print(key, " ".join("%s=%.2f" % kv for kv in avg.items()))
-apath = os.path.join(ROOT, "gpurun_out", "attn_trace.bin")
-has_attn = hasattr(lib, "vcl_debug_attn_trace_dump")   # only in builds with the attention trace hook
-if has_attn and lib.vcl_debug_attn_trace_dump(apath.encode()) == 0:
-    ar = np.fromfile(apath, dtype=np.uint64)
-    an, ac = int(ar[0]), int(ar[1])
-    at = ar[2:].reshape(-1, ac, 8).astype(np.int64)[an - L:an]          # last step: one launch per layer
-    rows_a = []
-    for l in range(1, L):
-        a = at[l]
-        qkv_end = recs[4 * l][:, 4].max(); o_wait = recs[4 * l + 1][:, 1].min()
-        rows_a.append(dict(entry_before_qkv_end=(qkv_end - a[:, 0].max()) / 1e3, qkv_end_to_wait=(a[:, 1].min() - qkv_end) / 1e3,
-                           wait_to_q=(a[:, 4] - a[:, 1]).mean() / 1e3, q_to_scores=(a[:, 5] - a[:, 4]).mean() / 1e3,
-                           scores_to_sync1=(a[:, 2] - a[:, 5]).mean() / 1e3, sync1=(a[:, 6] - a[:, 2]).mean() / 1e3,
-                           pv=(a[:, 7] - a[:, 6]).mean() / 1e3, sync2_write=(a[:, 3] - a[:, 7]).mean() / 1e3,
-                           total_after_wait=(a[:, 3].max() - a[:, 1].min()) / 1e3, end_to_o_wait=(o_wait - a[:, 3].max()) / 1e3))
-    print("attention", " ".join("%s=%.2f" % (k, float(np.mean([r[k] for r in rows_a]))) for k in rows_a[0]))
-lay = [(recs[4 * (l + 1)][:, 1].min() - recs[4 * l][:, 1].min()) / 1e3 for l in range(L - 1)]
-print("per-layer us", [round(x, 1) for x in lay])
+t0 = recs[0][:, 0, 0].min()
+print("fused" if fused else "unfused", "step span us", (recs[-1][:, :, 4].max() - t0) / 1e3, "launches", per_step)
+if fused:
+    # launches 1..L: [o_proj, gate/up, down, next q|k|v or logits]
+    for ph in range(4):
+        rows = []
+        for k in range(2, L):            # layers 1..L-2 (phase 3 = q|k|v)
+            r = recs[k][:, ph, :]
+            prev_end = recs[k][:, ph - 1, 4] if ph > 0 else None
+            d = dict(x_stage=(r[:, 2] - r[:, 1]).mean() / 1e3, stream=(r[:, 3] - r[:, 2]).mean() / 1e3,
+                     stream_max=(r[:, 3].max() - r[:, 2].min()) / 1e3, epi=(r[:, 4] - r[:, 3]).mean() / 1e3,
+                     barrier=((r[:, 1] - prev_end).mean() / 1e3 if ph > 0 else 0.0),
+                     barrier_last_arrival_to_release=((r[:, 1].min() - prev_end.max()) / 1e3 if ph > 0 else 0.0),
+                     phase_total=(r[:, 4].max() - (prev_end.max() if ph > 0 else r[:, 1].min())) / 1e3,
+                     producer_ahead=(r[:, 3] - r[:, 6]).mean() / 1e3)
+            rows.append(d)
+        print("phase", ph, names[int(recs[2][0, ph, 7] >> 32)], " ".join("%s=%.2f" % (kk, float(np.mean([d[kk] for d in rows]))) for kk in rows[0]))
+    lay = [(recs[k + 1][:, 0, 1].min() - recs[k][:, 0, 1].min()) / 1e3 for k in range(1, L - 1)]
+    gaps = [(recs[k + 1][:, 0, 1].min() - recs[k][:, 3, 4].max()) / 1e3 for k in range(1, L - 1)]
+    print("per-layer us", [round(x, 1) for x in lay])
+    print("fused-kernel end -> next fused kernel's dependency resolved (attention in between) us", [round(x, 1) for x in gaps])
+else:
+    for k in range(4, per_step, max(1, (per_step - 4) // 8)):
+        r = recs[k][:, 0, :]
+        print(k, names[int(r[0, 7] >> 32)], "x_stage %.2f stream %.2f/%.2f epi %.2f" % ((r[:, 2] - r[:, 1]).mean() / 1e3, (r[:, 3] - r[:, 2]).mean() / 1e3,
+              (r[:, 3].max() - r[:, 2].min()) / 1e3, (r[:, 4] - r[:, 3]).mean() / 1e3))
+    lay = [(recs[4 * (l + 1)][:, 0, 1].min() - recs[4 * l][:, 0, 1].min()) / 1e3 for l in range(L - 1)]
+    print("per-layer us", [round(x, 1) for x in lay])
 sys.stdout.flush()
 os._exit(0)

@@ -46,7 +46,6 @@ namespace vcl {
 
 namespace {
 
-enum { MODE_RES = 0, MODE_SWIGLU = 1, MODE_QKV = 2, MODE_LOGITS = 3 };
 constexpr int TC_CWARPS = 8;
 constexpr int TC_CONSUMERS = TC_CWARPS * 32;
 constexpr int TC_THREADS = TC_CONSUMERS + 32;
@@ -56,19 +55,19 @@ constexpr int TC_MAX_SLOTS = 8;                     // measured optimum (7 B sha
 constexpr int TC_SMEM_BUDGET = 160 * 1024;          // one CTA per SM; the rest of the SM stays free for the
                                                     // attention kernel's CTAs, which launch early (PDL)
 
+constexpr int TC_MAX_PHASES = 4;
+
 struct TcParams {
-  const bf16* x;
-  const bf16* W;                    // tiled copy (gemv_tc_repack)
-  int N, K;
+  TcPhase ph[TC_MAX_PHASES];        // dependent projections executed back to back by one launch
+  int n_phases;
   int n_slots;
-  const bf16* norm_w; float eps;
-  bf16* out;                        // RES: [N]; SWIGLU: [N/2]
-  const bf16* res;
-  bf16* q_out; bf16* kcache; bf16* vcache;
+  int x_elems;                      // max K over the phases (activation buffer)
+  int r_cap;                        // max rows one CTA owns in a phase (result buffer)
+  float eps;
   const bf16* cos_t; const bf16* sin_t;
   int H, s_max, pos;
-  float* logits;
-  unsigned long long* trace;        // optional [grid][8] timestamps (VCL_TC_TRACE), else nullptr
+  unsigned* gen_counter;            // launch generation of the tagged hand-off buffers (multi-phase launches)
+  unsigned long long* trace;        // optional [grid][TC_MAX_PHASES][8] timestamps (VCL_TC_TRACE)
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -99,36 +98,19 @@ __device__ __forceinline__ void tc_mma(float (&c)[4], uint32_t a0, uint32_t a1, 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// virtual row -> weight row. QKV: the rows of a RoPE pair (d, d+64) are made adjacent (2p, 2p+1)
-template <int MODE>
-__device__ __forceinline__ long long map_row(int v) {
-  if (MODE == MODE_QKV) return (long long)(v >> 7) * 128 + ((v & 127) >> 1) + (((v & 127) & 1) << 6);
-  return v;
+// virtual q/k/v row -> weight row: the rows of a RoPE pair (d, d+64) are made adjacent (2p, 2p+1)
+__device__ __forceinline__ long long qkv_row(int v) {
+  return (long long)(v >> 7) * 128 + ((v & 127) >> 1) + (((v & 127) & 1) << 6);
 }
 
-template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // layout: ring[n_slots] | x[K] bf16 | pbuf[2][TC_CWARPS][16] | result[r_cap] fp32 | red | barriers
-  const int K = p.K, N = p.N;
+  // layout: ring[n_slots] | x[x_elems] bf16 | pbuf[2][TC_CWARPS][16] | result[r_cap] fp32 | red | barriers
   const int n_slots = p.n_slots;
-  const int n_groups = (N + 15) >> 4;
-  const int nkc = (K + TC_KC - 1) / TC_KC;
-  // contiguous blocks of 16-row groups per CTA, sizes differing by at most one group. (Cutting the
-  // matrix into equal SLOT shares with partial sums exchanged between neighbours - stream-K - was
-  // measured: every CTA then streams the same bytes, but the kernels got 9 % slower; per-SM
-  // throughput is latency-bound, not bandwidth-shared, so the early finishers were not the problem.)
-  const int grp_begin = (int)(((long long)blockIdx.x * n_groups) / gridDim.x);
-  const int grp_end = (int)(((long long)(blockIdx.x + 1) * n_groups) / gridDim.x);
-  const int my_groups = grp_end - grp_begin;
-  const int R = my_groups * 16;                      // local rows (the last group may be partial)
-  const int row0 = grp_begin * 16;
-
   bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_slots * TC_SLOT_BYTES);
-  float* pbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)K * 2);
+  float* pbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)p.x_elems * 2);
   float* result = pbuf + 2 * TC_CWARPS * 16;
-  const int r_cap = ((n_groups + gridDim.x - 1) / gridDim.x) * 16;     // same on every CTA (layout)
-  float* red = result + r_cap;
+  float* red = result + p.r_cap;
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16);
   const uint32_t ring0 = smem_u32(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -136,187 +118,326 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
   auto empty_bar = [&](int s) { return bar0 + 8u * (TC_MAX_SLOTS + s); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  auto trace = [&](int ev) { if (p.trace != nullptr) p.trace[blockIdx.x * 8 + ev] = globaltimer_ns(); };
+  auto trace = [&](int phase, int ev) {
+    if (p.trace != nullptr) p.trace[((size_t)blockIdx.x * TC_MAX_PHASES + phase) * 8 + ev] = globaltimer_ns();
+  };
   if (tid == 0) {
-    trace(0);
+    trace(0, 0);
     for (int s = 0; s < n_slots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), TC_CWARPS); }
     mbar_fence_init();
   }
   __syncthreads();
-  pdl_launch_dependents();                           // the next kernel may take the other half of the SM
+  pdl_launch_dependents();                           // the next kernel (attention) may become resident
 
   int slot = 0;
   uint32_t par = 0;
   auto advance = [&]() { if (++slot == n_slots) { slot = 0; par ^= 1u; } };
+  // contiguous blocks of 16-row groups per CTA, sizes differing by at most one group. (Cutting the
+  // matrix into equal SLOT shares with partial sums exchanged between neighbours - stream-K - was
+  // measured: every CTA then streams the same bytes, but the kernels got 9 % slower.)
+  auto my_groups = [&](int N, int& grp_begin) {
+    const int n_groups = (N + 15) >> 4;
+    grp_begin = (int)(((long long)blockIdx.x * n_groups) / gridDim.x);
+    return (int)(((long long)(blockIdx.x + 1) * n_groups) / gridDim.x) - grp_begin;
+  };
 
   if (warp == TC_CWARPS) {
     // =============================== producer ===============================
+    // streams the weights of ALL phases in order; it never waits for a phase to finish, so HBM
+    // keeps streaming while the consumers run an epilogue, sit in the grid barrier or fetch the
+    // next activation vector
     if (lane == 0) {
-      trace(5);
-      for (int g = 0; g < my_groups; ++g) {
-        const bf16* src = p.W + (size_t)(grp_begin + g) * 16 * K;
-        for (int kc = 0; kc < nkc; ++kc) {
-          const uint32_t bytes = (uint32_t)min(TC_KC, K - kc * TC_KC) * 32u;      // 16 rows x 2 B
-          mbar_wait(empty_bar(slot), par ^ 1u);
-          mbar_arrive_expect_tx(full_bar(slot), bytes);
-          bulk_g2s(ring0 + slot * TC_SLOT_BYTES, src + (size_t)kc * TC_KC * 16, bytes, full_bar(slot));
-          advance();
+      for (int i = 0; i < p.n_phases; ++i) {
+        const TcPhase& ph = p.ph[i];
+        const int K = ph.K, nkc = (K + TC_KC - 1) / TC_KC;
+        int grp_begin;
+        const int ng = my_groups(ph.N, grp_begin);
+        trace(i, 5);
+        for (int g = 0; g < ng; ++g) {
+          const bf16* src = ph.W_tiled + (size_t)(grp_begin + g) * 16 * K;
+          for (int kc = 0; kc < nkc; ++kc) {
+            const uint32_t bytes = (uint32_t)min(TC_KC, K - kc * TC_KC) * 32u;    // 16 rows x 2 B
+            mbar_wait(empty_bar(slot), par ^ 1u);
+            mbar_arrive_expect_tx(full_bar(slot), bytes);
+            bulk_g2s(ring0 + slot * TC_SLOT_BYTES, src + (size_t)kc * TC_KC * 16, bytes, full_bar(slot));
+            advance();
+          }
         }
+        trace(i, 6);
       }
-      trace(6);
     }
     return;
   }
 
   // =============================== consumers ===============================
-  // Activation vector -> shared memory (bf16), RMS-normalised when the layer norm is fused. The
-  // dependent latency after the wait is ONE L2 round trip: the norm weights (constants) are
-  // parked in the x buffer before the wait, and every thread issues all its x loads back to back.
   constexpr int XU = 7;                               // 16-byte chunks per thread: K <= 14336
-  const int nch = K >> 3;
-  if (p.norm_w != nullptr) {
-#pragma unroll
-    for (int i = 0; i < XU; ++i) {
-      const int c = tid + i * TC_CONSUMERS;
-      if (c < nch) *reinterpret_cast<uint4*>(xs + c * 8) = __ldg(reinterpret_cast<const uint4*>(p.norm_w + c * 8));
-    }
-  }
-  pdl_wait();                                        // the activation vector comes from the previous kernel
-  if (tid == 0) trace(1);
-  {
-    uint4 xv[XU];
-#pragma unroll
-    for (int i = 0; i < XU; ++i) {
-      const int c = tid + i * TC_CONSUMERS;
-      xv[i] = (c < nch) ? ld_cg_v4(p.x + c * 8) : make_uint4(0, 0, 0, 0);
-    }
-    if (p.norm_w != nullptr) {
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < XU; ++i) {
-        const uint4 u = xv[i];
-        const float f0 = bf16lo(u.x), f1 = bf16hi(u.x), f2 = bf16lo(u.y), f3 = bf16hi(u.y);
-        const float f4 = bf16lo(u.z), f5 = bf16hi(u.z), f6 = bf16lo(u.w), f7 = bf16hi(u.w);
-        ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
-      }
-      ss = warp_sum(ss);
-      if (lane == 0) red[warp] = ss;
-      cbar();
-      float tot = 0.f;
-#pragma unroll
-      for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
-      const float rstd = rsqrtf(tot / (float)K + p.eps);
-#pragma unroll
-      for (int i = 0; i < XU; ++i) {
-        const int c = tid + i * TC_CONSUMERS;
-        if (c < nch) {
-          const uint4 u = xv[i];
-          const uint4 gw = *reinterpret_cast<const uint4*>(xs + c * 8);
-          uint4 o;
-          // w * bf16(x * rstd), the product rounded to bf16 again (LlamaRMSNorm)
-          o.x = bf16x2_mul(gw.x, pack_bf16x2(bf16lo(u.x) * rstd, bf16hi(u.x) * rstd));
-          o.y = bf16x2_mul(gw.y, pack_bf16x2(bf16lo(u.y) * rstd, bf16hi(u.y) * rstd));
-          o.z = bf16x2_mul(gw.z, pack_bf16x2(bf16lo(u.z) * rstd, bf16hi(u.z) * rstd));
-          o.w = bf16x2_mul(gw.w, pack_bf16x2(bf16lo(u.w) * rstd, bf16hi(u.w) * rstd));
-          *reinterpret_cast<uint4*>(xs + c * 8) = o;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < XU; ++i) {
-        const int c = tid + i * TC_CONSUMERS;
-        if (c < nch) *reinterpret_cast<uint4*>(xs + c * 8) = xv[i];
-      }
-    }
-    cbar();
-  }
-  if (tid == 0) trace(2);
-
   const int g = lane >> 2, q = lane & 3;
-  for (int grp = 0; grp < my_groups; ++grp) {
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int kc = 0; kc < nkc; ++kc) {
-      const int kb_n = min(TC_KC, K - kc * TC_KC) >> 5;          // 32-wide K blocks in this slot
-      mbar_wait(full_bar(slot), par);
-      const uint8_t* base = smem + slot * TC_SLOT_BYTES;
+  unsigned gen = 0;
+  for (int i = 0; i < p.n_phases; ++i) {
+    const TcPhase& ph = p.ph[i];
+    const int K = ph.K, N = ph.N, mode = ph.mode;
+    const int nkc = (K + TC_KC - 1) / TC_KC;
+    const int nch = K >> 3;
+    int grp_begin;
+    const int ng = my_groups(N, grp_begin);
+    const int row0 = grp_begin * 16;
+    // Activation vector -> shared memory (bf16), RMS-normalised when the layer norm is fused. The
+    // norm weights (constants) are parked in the x buffer first, every thread issues its x loads back
+    // to back: the dependent latency is one L2 round trip.
+    if (ph.norm_w != nullptr) {
 #pragma unroll
-      for (int t = 0; t < TC_KC / 32 / TC_CWARPS; ++t) {
-        const int kb = warp + TC_CWARPS * t;
-        if (kb < kb_n) {
-          const uint4 wa = *reinterpret_cast<const uint4*>(base + kb * 1024 + lane * 16);        // row g
-          const uint4 wb = *reinterpret_cast<const uint4*>(base + kb * 1024 + 512 + lane * 16);  // row g+8
-          uint4 xq = make_uint4(0, 0, 0, 0);
-          if (g == 0) xq = *reinterpret_cast<const uint4*>(xs + kc * TC_KC + kb * 32 + q * 8);
-          tc_mma(c, wa.x, wb.x, wa.y, wb.y, xq.x, xq.y);
-          tc_mma(c, wa.z, wb.z, wa.w, wb.w, xq.z, xq.w);
+      for (int u = 0; u < XU; ++u) {
+        const int c = tid + u * TC_CONSUMERS;
+        if (c < nch) *reinterpret_cast<uint4*>(xs + c * 8) = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + c * 8));
+      }
+    }
+    float ss = 0.f;
+    if (i == 0) {
+      pdl_wait();                                    // the first activation vector comes from the previous kernel
+      if (tid == 0) {
+        trace(i, 1);
+        if (p.n_phases > 1) {
+          unsigned b;
+          asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(b) : "l"(p.gen_counter) : "memory");
+          red[8] = __uint_as_float(b);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(slot));
-      advance();
+      uint4 xv[XU];
+#pragma unroll
+      for (int u = 0; u < XU; ++u) {
+        const int c = tid + u * TC_CONSUMERS;
+        xv[u] = (c < nch) ? ld_cg_v4(ph.x + c * 8) : make_uint4(0, 0, 0, 0);
+      }
+      if (ph.norm_w != nullptr) {
+#pragma unroll
+        for (int u = 0; u < XU; ++u) {
+          const uint4 v = xv[u];
+          const float f0 = bf16lo(v.x), f1 = bf16hi(v.x), f2 = bf16lo(v.y), f3 = bf16hi(v.y);
+          const float f4 = bf16lo(v.z), f5 = bf16hi(v.z), f6 = bf16lo(v.w), f7 = bf16hi(v.w);
+          ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[warp] = ss;
+        cbar();
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
+        const float rstd = rsqrtf(tot / (float)K + p.eps);
+#pragma unroll
+        for (int u = 0; u < XU; ++u) {
+          const int c = tid + u * TC_CONSUMERS;
+          if (c < nch) {
+            const uint4 v = xv[u];
+            const uint4 gw = *reinterpret_cast<const uint4*>(xs + c * 8);
+            uint4 o;
+            // w * bf16(x * rstd), the product rounded to bf16 again (LlamaRMSNorm)
+            o.x = bf16x2_mul(gw.x, pack_bf16x2(bf16lo(v.x) * rstd, bf16hi(v.x) * rstd));
+            o.y = bf16x2_mul(gw.y, pack_bf16x2(bf16lo(v.y) * rstd, bf16hi(v.y) * rstd));
+            o.z = bf16x2_mul(gw.z, pack_bf16x2(bf16lo(v.z) * rstd, bf16hi(v.z) * rstd));
+            o.w = bf16x2_mul(gw.w, pack_bf16x2(bf16lo(v.w) * rstd, bf16hi(v.w) * rstd));
+            *reinterpret_cast<uint4*>(xs + c * 8) = o;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < XU; ++u) {
+          const int c = tid + u * TC_CONSUMERS;
+          if (c < nch) *reinterpret_cast<uint4*>(xs + c * 8) = xv[u];
+        }
+      }
+      cbar();
+    } else {
+      // ---- phase i reads what every CTA wrote in phase i-1: tagged hand-off, no barrier, no fence ----
+      // The producers of the vector store 8-byte units {bf16 v0, bf16 v1, u32 generation} with ONE
+      // 64-bit store each (single-copy atomic), the consumers poll every unit until its generation is
+      // the expected one: a unit is either entirely old or entirely new, so no memory fence is needed
+      // (a gpu-scope fence costs ~3 us here while bulk copies are in flight) and a CTA waits exactly
+      // for the data it reads. All CTAs of the launch are resident (a CTA takes more than half an SM
+      // and the next launch cannot start before every CTA of this one has started).
+      const unsigned want = __float_as_uint(red[8]) * 8u + (unsigned)i;
+      const int n_units = K >> 1;
+      // Waiting is done by ONE warp on ONE unit per producing CTA (the last unit of its block), with
+      // a pause between polls: when every thread polls the units it needs, ~38 000 pollers queue up
+      // on the two or three L2 lines the slowest CTA has still to write and slow down that very CTA.
+      // The per-unit generation check below stays (it is what makes the hand-off correct); after
+      // this it practically never has to spin.
+      if (warp == 0) {
+        const TcPhase& prev = p.ph[i - 1];
+        const int pg = (prev.N + 15) >> 4;
+        for (int cta = lane; cta < (int)gridDim.x; cta += 32) {
+          const int ge = (int)(((long long)(cta + 1) * pg) / gridDim.x);            // end of that CTA's row groups
+          const int elem_end = (prev.mode == TC_MODE_RES) ? ge * 16 : ge * 8;
+          const unsigned long long* sentinel = ph.x_tagged + ((elem_end - 2) >> 1);
+          unsigned long long v;
+          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(sentinel) : "memory");
+          for (int spin = 0; (unsigned)(v >> 32) != want && spin < (1 << 19); ++spin) {
+            __nanosleep(64);
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(sentinel) : "memory");
+          }
+        }
+      }
+      cbar();
+      constexpr int UB = 12;                          // units per thread and batch (K <= 6144 in one batch)
+      const bool normed = ph.norm_w != nullptr;      // (normed phases have K = hidden size: one batch)
+      for (int u0 = 0; u0 < n_units; u0 += UB * TC_CONSUMERS) {
+        unsigned long long uv[UB];
+#pragma unroll
+        for (int b = 0; b < UB; ++b) {
+          const int u = u0 + tid + b * TC_CONSUMERS;
+          uv[b] = 0;
+          if (u < n_units) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(uv[b]) : "l"(ph.x_tagged + u) : "memory");
+        }
+#pragma unroll
+        for (int b = 0; b < UB; ++b) {
+          const int u = u0 + tid + b * TC_CONSUMERS;
+          if (u < n_units) {
+            // (bounded: a protocol bug must show up as a wrong result in the tests, never as a hung GPU)
+            for (int spin = 0; (unsigned)(uv[b] >> 32) != want && spin < (1 << 21); ++spin)
+              asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(uv[b]) : "l"(ph.x_tagged + u) : "memory");
+            const uint32_t v = (uint32_t)uv[b];
+            if (!normed) {
+              *reinterpret_cast<uint32_t*>(xs + 2 * u) = v;
+            } else {
+              const float f0 = bf16lo(v), f1 = bf16hi(v);
+              ss += f0 * f0 + f1 * f1;
+            }
+          }
+        }
+        if (normed) {
+          ss = warp_sum(ss);
+          if (lane == 0) red[warp] = ss;
+          cbar();
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
+          const float rstd = rsqrtf(tot / (float)K + p.eps);
+#pragma unroll
+          for (int b = 0; b < UB; ++b) {
+            const int u = u0 + tid + b * TC_CONSUMERS;
+            if (u < n_units) {
+              const uint32_t v = (uint32_t)uv[b];
+              const uint32_t gw = *reinterpret_cast<const uint32_t*>(xs + 2 * u);
+              *reinterpret_cast<uint32_t*>(xs + 2 * u) = bf16x2_mul(gw, pack_bf16x2(bf16lo(v) * rstd, bf16hi(v) * rstd));
+            }
+          }
+        }
+      }
+      if (tid == 0) trace(i, 1);
+      cbar();
     }
-    // the 8 per-warp partials of this row group meet in shared memory (double-buffered: the barrier of
-    // the next group orders the reads below before the buffer is written again)
-    float* pb = pbuf + (grp & 1) * TC_CWARPS * 16;
-    if (q == 0) {                                     // column 0: rows g (c[0]) and g+8 (c[2])
-      pb[warp * 16 + g] = c[0];
-      pb[warp * 16 + g + 8] = c[2];
+    if (tid == 0) trace(i, 2);
+
+    for (int grp = 0; grp < ng; ++grp) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int kc = 0; kc < nkc; ++kc) {
+        const int kb_n = min(TC_KC, K - kc * TC_KC) >> 5;        // 32-wide K blocks in this slot
+        mbar_wait(full_bar(slot), par);
+        const uint8_t* base = smem + slot * TC_SLOT_BYTES;
+#pragma unroll
+        for (int t = 0; t < TC_KC / 32 / TC_CWARPS; ++t) {
+          const int kb = warp + TC_CWARPS * t;
+          if (kb < kb_n) {
+            const uint4 wa = *reinterpret_cast<const uint4*>(base + kb * 1024 + lane * 16);        // row g
+            const uint4 wb = *reinterpret_cast<const uint4*>(base + kb * 1024 + 512 + lane * 16);  // row g+8
+            uint4 xq = make_uint4(0, 0, 0, 0);
+            if (g == 0) xq = *reinterpret_cast<const uint4*>(xs + kc * TC_KC + kb * 32 + q * 8);
+            tc_mma(c, wa.x, wb.x, wa.y, wb.y, xq.x, xq.y);
+            tc_mma(c, wa.z, wb.z, wa.w, wb.w, xq.z, xq.w);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(slot));
+        advance();
+      }
+      // the 8 per-warp partials of this row group meet in shared memory (double-buffered: the barrier
+      // of the next group orders the reads below before the buffer is written again)
+      float* pb = pbuf + (grp & 1) * TC_CWARPS * 16;
+      if (q == 0) {                                   // column 0: rows g (c[0]) and g+8 (c[2])
+        pb[warp * 16 + g] = c[0];
+        pb[warp * 16 + g + 8] = c[2];
+      }
+      cbar();
+      if (tid < 16) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < TC_CWARPS; ++w) v += pb[w * 16 + tid];
+        result[grp * 16 + tid] = v;
+      }
     }
     cbar();
-    if (tid < 16) {
-      float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < TC_CWARPS; ++w) v += pb[w * 16 + tid];
-      result[grp * 16 + tid] = v;
-    }
-  }
-  cbar();
-  if (tid == 0) trace(3);
+    if (tid == 0) trace(i, 3);
 
-  // ---------------- epilogue: combine the 8 warp partials ----------------
-  constexpr bool PAIRS = (MODE == MODE_SWIGLU || MODE == MODE_QKV);
-  const int n_items = PAIRS ? R / 2 : R;
-  for (int it = tid; it < n_items; it += TC_CONSUMERS) {
-    const int rr = PAIRS ? 2 * it : it;
-    const int vrow = row0 + rr;
-    if (vrow >= N) continue;
-    const float v0 = result[rr];
-    const float v1 = PAIRS ? result[rr + 1] : 0.f;
-    if (MODE == MODE_RES) {
-      float y = bf16r(v0);
-      if (p.res != nullptr) y += __bfloat162float(p.res[vrow]);
-      p.out[vrow] = __float2bfloat16_rn(y);
-    } else if (MODE == MODE_LOGITS) {
-      p.logits[vrow] = bf16r(v0);
-    } else if (MODE == MODE_SWIGLU) {
-      const float gt = bf16r(v0);
-      const float sg = bf16r(__fdividef(gt, 1.0f + __expf(-gt)));
-      p.out[vrow >> 1] = __float2bfloat16_rn(sg * bf16r(v1));
-    } else {  // MODE_QKV: vrow = (which*H + head)*128 + 2*d
-      const int hr = vrow >> 7;
-      const int which = hr / p.H, head = hr - which * p.H;
-      const int d = (vrow & 127) >> 1;
-      const float lo = bf16r(v0), hi = bf16r(v1);
-      const long long coff = ((long long)head * p.s_max + p.pos) * 128;
-      if (which == 2) {
-        p.vcache[coff + d] = __float2bfloat16_rn(lo);
-        p.vcache[coff + d + 64] = __float2bfloat16_rn(hi);
-      } else {
-        const float cs = __bfloat162float(p.cos_t[(long long)p.pos * 64 + d]);
-        const float sn = __bfloat162float(p.sin_t[(long long)p.pos * 64 + d]);
-        const float olo = bf16r(lo * cs) + bf16r(-hi * sn);
-        const float ohi = bf16r(hi * cs) + bf16r(lo * sn);
-        if (which == 0) {
-          p.q_out[head * 128 + d] = __float2bfloat16_rn(olo);
-          p.q_out[head * 128 + d + 64] = __float2bfloat16_rn(ohi);
-        } else {
-          p.kcache[coff + d] = __float2bfloat16_rn(olo);
-          p.kcache[coff + d + 64] = __float2bfloat16_rn(ohi);
+    // ---------------- fused epilogue ----------------
+    const bool pairs = (mode == TC_MODE_SWIGLU || mode == TC_MODE_QKV);
+    const int R = ng * 16;
+    const int n_items = pairs ? R / 2 : R;
+    const unsigned tag_out = (p.n_phases > 1 ? __float_as_uint(red[8]) * 8u : 0u) + (unsigned)i + 1u;
+    for (int it0 = 0; it0 < n_items; it0 += TC_CONSUMERS) {       // uniform trip count: the warps stay converged
+      const int it = it0 + tid;
+      const int rr = pairs ? 2 * it : it;
+      const int vrow = row0 + rr;
+      const bool valid = it < n_items && vrow < N;
+      float y = 0.f;                                 // RES / SWIGLU: the output value of this item
+      if (valid) {
+        const float v0 = result[rr];
+        const float v1 = pairs ? result[rr + 1] : 0.f;
+        if (mode == TC_MODE_RES) {
+          y = bf16r(v0);
+          if (ph.res != nullptr) {                    // may have been written by an earlier phase: read through L2
+            unsigned short rv;
+            asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(rv) : "l"(ph.res + vrow) : "memory");
+            y += __uint_as_float((uint32_t)rv << 16);
+          }
+          ph.out[vrow] = __float2bfloat16_rn(y);
+        } else if (mode == TC_MODE_LOGITS) {
+          ph.logits[vrow] = bf16r(v0);
+        } else if (mode == TC_MODE_SWIGLU) {
+          const float gt = bf16r(v0);
+          const float sg = bf16r(__fdividef(gt, 1.0f + __expf(-gt)));
+          y = sg * bf16r(v1);
+          ph.out[vrow >> 1] = __float2bfloat16_rn(y);
+        } else {  // TC_MODE_QKV: vrow = (which*H + head)*128 + 2*d
+          const int hr = vrow >> 7;
+          const int which = hr / p.H, head = hr - which * p.H;
+          const int d = (vrow & 127) >> 1;
+          const float lo = bf16r(v0), hi = bf16r(v1);
+          const long long coff = ((long long)head * p.s_max + p.pos) * 128;
+          if (which == 2) {
+            ph.vcache[coff + d] = __float2bfloat16_rn(lo);
+            ph.vcache[coff + d + 64] = __float2bfloat16_rn(hi);
+          } else {
+            const float cs = __bfloat162float(p.cos_t[(long long)p.pos * 64 + d]);
+            const float sn = __bfloat162float(p.sin_t[(long long)p.pos * 64 + d]);
+            const float olo = bf16r(lo * cs) + bf16r(-hi * sn);
+            const float ohi = bf16r(hi * cs) + bf16r(lo * sn);
+            if (which == 0) {
+              ph.q_out[head * 128 + d] = __float2bfloat16_rn(olo);
+              ph.q_out[head * 128 + d + 64] = __float2bfloat16_rn(ohi);
+            } else {
+              ph.kcache[coff + d] = __float2bfloat16_rn(olo);
+              ph.kcache[coff + d + 64] = __float2bfloat16_rn(ohi);
+            }
+          }
+        }
+      }
+      if (ph.out_tagged != nullptr) {
+        // the hand-off copy for the next phase: items (2j, 2j+1) of a warp form one 8-byte unit
+        // {value 2j, value 2j+1, generation}; item k is output element (row0 + k) of RES,
+        // (row0 / 2 + k) of SWIGLU
+        const float y1 = __shfl_down_sync(0xffffffffu, y, 1);
+        if (valid && (it & 1) == 0) {
+          const int elem = (mode == TC_MODE_RES) ? vrow : (vrow >> 1);
+          ph.out_tagged[elem >> 1] = ((unsigned long long)tag_out << 32) | pack_bf16x2(y, y1);
         }
       }
     }
+    if (tid == 0) {
+      trace(i, 4);
+      if (p.trace != nullptr) p.trace[((size_t)blockIdx.x * TC_MAX_PHASES + i) * 8 + 7] = ((unsigned long long)mode << 32) | (unsigned)N;
+    }
   }
-  if (tid == 0) { trace(4); if (p.trace != nullptr) p.trace[blockIdx.x * 8 + 7] = ((unsigned long long)MODE << 32) | (unsigned)N; }
+  // next multi-phase launch uses the next generation (it reads the counter after its dependency wait)
+  if (p.n_phases > 1 && blockIdx.x == 0 && tid == 0) *p.gen_counter = __float_as_uint(red[8]) + 1u;
 }
 
 // row-major W[N][K] -> tiled copy. One thread per 16-byte chunk of the output.
@@ -334,19 +455,25 @@ __global__ void gemv_tc_repack_kernel(const bf16* __restrict__ W, bf16* __restri
     const int k = kc * TC_KC + kb * 32 + (l & 3) * 8;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (row < N) {
-      const long long src_row = qkv ? map_row<MODE_QKV>(row) : (long long)row;
+      const long long src_row = qkv ? qkv_row(row) : (long long)row;
       v = *reinterpret_cast<const uint4*>(W + src_row * K + k);
     }
     *reinterpret_cast<uint4*>(dst + o * 8) = v;
   }
 }
 
-// shared-memory plan for (N, K) on `grid` CTAs; returns the slot count (0 = does not fit)
-int plan(int N, int K, int grid, size_t* smem_bytes) {
-  const int n_groups = (N + 15) / 16;
-  if (n_groups < grid) return 0;                     // every CTA streams at least one row group
-  const int r_cap = ((n_groups + grid - 1) / grid) * 16;
-  const size_t fixed = (size_t)K * 2 + (size_t)(2 * TC_CWARPS * 16 + r_cap) * 4 + 16 * 4 + 2 * TC_MAX_SLOTS * 8 + 128;
+// shared-memory plan for a chain of phases on `grid` CTAs; returns the slot count (0 = does not fit)
+int plan(const TcPhase* ph, int n, int grid, size_t* smem_bytes, int* x_elems, int* r_cap) {
+  int kmax = 0, rmax = 0;
+  for (int i = 0; i < n; ++i) {
+    const int n_groups = (ph[i].N + 15) / 16;
+    if (n_groups < grid) return 0;                   // every CTA streams at least one row group
+    if (ph[i].K % 32 != 0 || ph[i].K > 14336) return 0;
+    kmax = ph[i].K > kmax ? ph[i].K : kmax;
+    const int r = ((n_groups + grid - 1) / grid) * 16;
+    rmax = r > rmax ? r : rmax;
+  }
+  const size_t fixed = (size_t)kmax * 2 + (size_t)(2 * TC_CWARPS * 16 + rmax) * 4 + 16 * 4 + 2 * TC_MAX_SLOTS * 8 + 128;
   static const int env_slots = getenv("VCL_GEMV_TC_SLOTS") ? atoi(getenv("VCL_GEMV_TC_SLOTS")) : 0;
   static const size_t budget = getenv("VCL_GEMV_TC_SMEM_KB") ? (size_t)atoi(getenv("VCL_GEMV_TC_SMEM_KB")) * 1024 : (size_t)TC_SMEM_BUDGET;
   if (fixed + 2 * (size_t)TC_SLOT_BYTES > budget) return 0;
@@ -354,21 +481,61 @@ int plan(int N, int K, int grid, size_t* smem_bytes) {
   if (slots > TC_MAX_SLOTS) slots = TC_MAX_SLOTS;
   if (env_slots > 0 && env_slots < slots) slots = env_slots;
   *smem_bytes = (size_t)slots * TC_SLOT_BYTES + fixed;
+  *x_elems = kmax; *r_cap = rmax;
   return slots;
 }
 
-// VCL_TC_TRACE: every launch writes 8 timestamps per CTA into the next record of a device buffer;
-// vcl_debug_tc_trace_dump() (below) writes the records to a file. Debug aid for eager runs.
-constexpr int TC_TRACE_RECORDS = 1024;
+// VCL_TC_TRACE: every launch writes 8 timestamps per (CTA, phase) into the next record of a device
+// buffer; vcl_debug_tc_trace_dump() (below) writes the records to a file. Debug aid for eager runs.
+constexpr int TC_TRACE_RECORDS = 512;
 unsigned long long* g_trace = nullptr;
 int g_trace_next = 0;
+unsigned* g_gen = nullptr;            // generation counter of the tagged hand-off buffers (one stream)
 
-template <int MODE>
-int launch(TcParams p, cudaStream_t stream) {
+TcPhase phase_of(const GemvArgs& g, int mode) {
+  TcPhase ph;
+  ph.mode = mode; ph.W_tiled = g.W_tiled; ph.N = g.N; ph.K = g.K; ph.x = g.x; ph.norm_w = g.norm_w;
+  return ph;
+}
+
+}  // namespace
+
+bool gemv_tc_chain_supported(const TcPhase* ph, int n) {
+  static const bool off = getenv("VCL_GEMV_LEGACY") != nullptr;
+  if (off || n < 1 || n > TC_MAX_PHASES) return false;
+  for (int i = 0; i < n; ++i) {
+    if (ph[i].W_tiled == nullptr || ph[i].N < 16) return false;
+    if (((uintptr_t)ph[i].x % 16) != 0 || ((uintptr_t)ph[i].W_tiled % 16) != 0) return false;
+    if ((ph[i].mode == TC_MODE_SWIGLU || ph[i].mode == TC_MODE_QKV) && ph[i].N % 2 != 0) return false;
+  }
+  size_t smem = 0; int xe = 0, rc = 0;
+  return plan(ph, n, device_num_sms(), &smem, &xe, &rc) >= 2;
+}
+
+int launch_gemv_tc_chain(const TcPhase* ph, int n, const TcChainCommon& c, cudaStream_t stream) {
+  VCL_REQUIRE(n >= 1 && n <= TC_MAX_PHASES, "gemv_tc: %d phases (max %d)", n, TC_MAX_PHASES);
   const int grid = device_num_sms();
+  TcParams p = {};
+  for (int i = 0; i < n; ++i) p.ph[i] = ph[i];
+  p.n_phases = n; p.eps = c.eps; p.cos_t = c.cos_t; p.sin_t = c.sin_t; p.H = c.H; p.s_max = c.s_max; p.pos = c.pos;
+  size_t smem = 0;
+  p.n_slots = plan(ph, n, grid, &smem, &p.x_elems, &p.r_cap);
+  VCL_REQUIRE(p.n_slots >= 2, "gemv_tc: the phases (first N=%d K=%d) do not fit the shared-memory plan", ph[0].N, ph[0].K);
+  if (g_gen == nullptr) {
+    const unsigned one = 1;                          // generation 0 would match zero-initialised buffers
+    VCL_CUDA_OK(cudaMalloc(&g_gen, sizeof(unsigned)));
+    VCL_CUDA_OK(cudaMemcpy(g_gen, &one, sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
+  p.gen_counter = g_gen;
+  for (int i = 1; i < n; ++i) {
+    VCL_REQUIRE(ph[i].norm_w == nullptr || ph[i].K <= 6144, "gemv_tc: fused-norm phase %d with K=%d > 6144", i, ph[i].K);
+    VCL_REQUIRE(ph[i].x_tagged != nullptr && ph[i - 1].out_tagged != nullptr && ph[i - 1].N % 16 == 0 &&
+                    (ph[i - 1].mode == TC_MODE_RES || ph[i - 1].mode == TC_MODE_SWIGLU),
+                "gemv_tc: phase %d needs the tagged output of a residual / SwiGLU phase", i);
+  }
   static const bool tracing = getenv("VCL_TC_TRACE") != nullptr;
   if (tracing) {
-    const size_t rec = (size_t)grid * 8;
+    const size_t rec = (size_t)grid * TC_MAX_PHASES * 8;
     if (g_trace == nullptr) {
       VCL_CUDA_OK(cudaMalloc(&g_trace, TC_TRACE_RECORDS * rec * sizeof(unsigned long long)));
       VCL_CUDA_OK(cudaMemset(g_trace, 0, TC_TRACE_RECORDS * rec * sizeof(unsigned long long)));
@@ -376,9 +543,6 @@ int launch(TcParams p, cudaStream_t stream) {
     p.trace = g_trace + (size_t)(g_trace_next % TC_TRACE_RECORDS) * rec;
     ++g_trace_next;
   }
-  size_t smem = 0;
-  p.n_slots = plan(p.N, p.K, grid, &smem);
-  VCL_REQUIRE(p.n_slots >= 2, "gemv_tc: N=%d K=%d does not fit the shared-memory plan", p.N, p.K);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);
@@ -389,22 +553,17 @@ int launch(TcParams p, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemv_tc_kernel<MODE>, p));
+  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, gemv_tc_kernel, p));
   count_launches(1);
   return 0;
 }
 
-TcParams base(const GemvArgs& g) {
-  TcParams p = {};
-  p.x = g.x; p.W = g.W_tiled; p.N = g.N; p.K = g.K; p.norm_w = g.norm_w; p.eps = g.eps;
-  return p;
-}
-
+namespace {
 }  // namespace
 
 extern "C" int vcl_debug_tc_trace_dump(const char* path) {
   if (g_trace == nullptr) return -1;
-  const size_t n = (size_t)TC_TRACE_RECORDS * device_num_sms() * 8;
+  const size_t n = (size_t)TC_TRACE_RECORDS * device_num_sms() * TC_MAX_PHASES * 8;
   std::vector<unsigned long long> host(n + 2);
   VCL_CUDA_OK(cudaDeviceSynchronize());
   VCL_CUDA_OK(cudaMemcpy(host.data() + 2, g_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -417,20 +576,15 @@ extern "C" int vcl_debug_tc_trace_dump(const char* path) {
 }
 
 int init_gemv_tc_kernels() {
-  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel<MODE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel<MODE_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel<MODE_QKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel<MODE_LOGITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
   return 0;
 }
 
 // B = 1, 16-byte aligned operands, K a multiple of 32 and a shared-memory plan that fits
 bool gemv_tc_supported(const GemvArgs& g) {
-  static const bool off = getenv("VCL_GEMV_LEGACY") != nullptr;
-  if (off || g.B != 1 || g.W_tiled == nullptr || g.K % 32 != 0 || g.K > 14336 || g.N < 16) return false;
-  if (((uintptr_t)g.x % 16) != 0 || ((uintptr_t)g.W_tiled % 16) != 0) return false;
-  size_t smem = 0;
-  return plan(g.N, g.K, device_num_sms(), &smem) >= 2;
+  if (g.B != 1) return false;
+  const TcPhase ph = phase_of(g, TC_MODE_RES);
+  return gemv_tc_chain_supported(&ph, 1);
 }
 
 size_t gemv_tc_tiled_elems(int N, int K) { return (size_t)((N + 15) / 16) * 16 * K; }
@@ -444,30 +598,33 @@ int launch_gemv_tc_repack(const bf16* W, bf16* dst, int N, int K, bool qkv_pairs
 }
 
 int launch_gemv_tc_residual(const GemvArgs& g, bf16* out, const bf16* res, cudaStream_t stream) {
-  TcParams p = base(g);
-  p.out = out; p.res = res;
-  return launch<MODE_RES>(p, stream);
+  TcPhase ph = phase_of(g, TC_MODE_RES);
+  ph.out = out; ph.res = res;
+  TcChainCommon c; c.eps = g.eps;
+  return launch_gemv_tc_chain(&ph, 1, c, stream);
 }
 
 int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, cudaStream_t stream) {
   VCL_REQUIRE(g.N % 2 == 0, "gemv swiglu: N must be even (interleaved gate/up rows)");
-  TcParams p = base(g);
-  p.out = out;
-  return launch<MODE_SWIGLU>(p, stream);
+  TcPhase ph = phase_of(g, TC_MODE_SWIGLU);
+  ph.out = out;
+  TcChainCommon c; c.eps = g.eps;
+  return launch_gemv_tc_chain(&ph, 1, c, stream);
 }
 
 int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, bf16* kcache, bf16* vcache, const bf16* cos_t,
                             const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream) {
-  TcParams p = base(g);
-  p.q_out = q_out; p.kcache = kcache; p.vcache = vcache; p.cos_t = cos_t; p.sin_t = sin_t;
-  p.H = H; p.s_max = s_max; p.pos = pos;
-  return launch<MODE_QKV>(p, stream);
+  TcPhase ph = phase_of(g, TC_MODE_QKV);
+  ph.q_out = q_out; ph.kcache = kcache; ph.vcache = vcache;
+  TcChainCommon c; c.eps = g.eps; c.cos_t = cos_t; c.sin_t = sin_t; c.H = H; c.s_max = s_max; c.pos = pos;
+  return launch_gemv_tc_chain(&ph, 1, c, stream);
 }
 
 int launch_gemv_tc_logits(const GemvArgs& g, float* logits, cudaStream_t stream) {
-  TcParams p = base(g);
-  p.logits = logits;
-  return launch<MODE_LOGITS>(p, stream);
+  TcPhase ph = phase_of(g, TC_MODE_LOGITS);
+  ph.logits = logits;
+  TcChainCommon c; c.eps = g.eps;
+  return launch_gemv_tc_chain(&ph, 1, c, stream);
 }
 
 }  // namespace vcl

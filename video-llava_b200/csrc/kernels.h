@@ -143,6 +143,30 @@ int init_gemv_kernels();
 // ---- gemv_tc.cu : B = 1 variant (bulk-copy ring + mma.sync, two kernels co-resident per SM) ------
 // The launch_gemv_* entry points above route to these when gemv_tc_supported(g).
 int init_gemv_tc_kernels();
+// One launch can run up to 4 DEPENDENT projections back to back (o_proj -> gate/up -> down -> next
+// layer's q/k/v): the producer warp streams the weights of all phases without waiting, the consumers
+// separate the phases with a grid barrier, so HBM does not idle at those boundaries.
+enum { TC_MODE_RES = 0, TC_MODE_SWIGLU = 1, TC_MODE_QKV = 2, TC_MODE_LOGITS = 3 };
+struct TcPhase {
+  int mode = TC_MODE_RES;
+  const bf16* W_tiled = nullptr; int N = 0, K = 0;   // slot-ordered copy of the [N, K] matrix
+  const bf16* x = nullptr;                           // [K] input (written by the previous phase / kernel)
+  const bf16* norm_w = nullptr;                      // optional fused RMSNorm of x
+  bf16* out = nullptr; const bf16* res = nullptr;    // RES: out[N] (+res); SWIGLU: out[N/2]
+  bf16* q_out = nullptr; bf16* kcache = nullptr; bf16* vcache = nullptr;   // QKV (cache base of the layer)
+  float* logits = nullptr;                           // LOGITS: [N] bf16-rounded fp32
+  // hand-off between the phases of one launch: the same vector as `out` / `x`, as 8-byte units
+  // {bf16, bf16, u32 generation} (see gemv_tc.cu); x_tagged is read by every phase but the first
+  unsigned long long* out_tagged = nullptr;
+  const unsigned long long* x_tagged = nullptr;
+};
+struct TcChainCommon {
+  float eps = 0.f;
+  const bf16* cos_t = nullptr; const bf16* sin_t = nullptr;
+  int H = 0, s_max = 0, pos = 0;
+};
+bool gemv_tc_chain_supported(const TcPhase* ph, int n);
+int launch_gemv_tc_chain(const TcPhase* ph, int n, const TcChainCommon& c, cudaStream_t stream);
 bool gemv_tc_supported(const GemvArgs& g);
 size_t gemv_tc_tiled_elems(int N, int K);     // elements of the tiled copy of an [N, K] matrix
 // qkv_pairs: rows are taken in the order of the fused q/k/v kernel (RoPE pairs adjacent)

@@ -86,6 +86,7 @@ struct vcl_handle {
   MegaLayer* mega_layers = nullptr;            // device copy of the per-layer weight pointers
   float *att_stats = nullptr, *att_part = nullptr;
   unsigned int* mega_barrier = nullptr;
+  unsigned long long *h_tag = nullptr, *act_tag = nullptr;   // tagged hand-off copies of d_h / d_act (gemv_tc chains)
   bool use_mega = true;
   bool force_legacy_attention = false;
 
@@ -237,6 +238,12 @@ int vcl_create(vcl_handle** out, const vcl_config* c) {
   rc |= dalloc(h, &h->att_stats, Bm * c->llm_heads * 4 * 2);
   rc |= dalloc(h, &h->att_part, Bm * c->llm_heads * 4 * 128);
   rc |= dalloc(h, &h->mega_barrier, 32 * 17);
+  rc |= dalloc(h, &h->h_tag, (size_t)c->llm_hidden / 2 + 8);
+  rc |= dalloc(h, &h->act_tag, (size_t)c->llm_inter / 2 + 8);
+  if (rc == 0) {
+    cudaMemset(h->h_tag, 0, ((size_t)c->llm_hidden / 2 + 8) * 8);
+    cudaMemset(h->act_tag, 0, ((size_t)c->llm_inter / 2 + 8) * 8);
+  }
   rc |= dalloc(h, &h->mega_layers, (size_t)(c->llm_layers > 0 ? c->llm_layers : 1));
   if (rc == 0) rc = launch_rope_table(h->rope_cos, h->rope_sin, c->max_seq, 128, c->rope_theta, 0);
   if (rc == 0) {
@@ -562,6 +569,64 @@ int llm_decode_step(vcl_handle* h, const int32_t* tok_in, long long in_stride, i
     return 0;
   }
   VCL_TRY(launch_embed_tokens(tok_in, in_stride, h->embed, h->d_h, B, D, c.vocab, st));
+  // Opt-in experiment (VCL_DECODE_FUSED=1), single clip: two launches per layer. [q|k|v] -> attention ->
+  // [o_proj, gate/up, down, next layer's q|k|v (or the LM head)] ... : the dependent projections
+  // between two attention kernels run as phases of ONE gemv_tc launch with an in-kernel hand-off.
+  // Parity-green, but 8 % slower than one launch per projection (82 vs 74 ms per 31 steps): a
+  // programmatic dependent launch releases the next kernel ~1 us after the last CTA is done, the
+  // cheapest in-kernel hand-off measured (tagged 8-byte units, no fences) needs ~3 us, and the next
+  // kernel's ring is pre-filled in both cases. See profiles/r01_tc_trace.txt.
+  if (B == 1 && c.llm_layers > 0 && h->lm_head_t != nullptr && getenv("VCL_DECODE_FUSED") != nullptr) {
+    TcChainCommon cc;
+    cc.eps = c.rms_eps; cc.cos_t = h->rope_cos; cc.sin_t = h->rope_sin; cc.H = H; cc.s_max = c.max_seq; cc.pos = pos;
+    auto qkv_phase = [&](int l) {
+      TcPhase ph;
+      ph.mode = TC_MODE_QKV; ph.W_tiled = h->ll[l].wqkv_t; ph.N = 3 * D; ph.K = D; ph.x = h->d_h; ph.norm_w = h->ll[l].ln1;
+      ph.q_out = h->d_q; ph.kcache = kc_layer(h, l); ph.vcache = vc_layer(h, l);
+      return ph;
+    };
+    TcPhase chain[4];
+    chain[0] = qkv_phase(0);
+    bool ok = gemv_tc_chain_supported(chain, 1);
+    {
+      const LlmLayerW& w = h->ll[0];
+      chain[0].mode = TC_MODE_RES; chain[0].W_tiled = w.wo_t; chain[0].N = D; chain[0].K = D; chain[0].x = h->d_attn;
+      chain[0].norm_w = nullptr; chain[0].out = h->d_h; chain[0].res = h->d_h; chain[0].out_tagged = h->h_tag;
+      chain[1] = TcPhase(); chain[1].mode = TC_MODE_SWIGLU; chain[1].W_tiled = w.wgu_t; chain[1].N = 2 * F; chain[1].K = D;
+      chain[1].x = h->d_h; chain[1].x_tagged = h->h_tag; chain[1].norm_w = w.ln2; chain[1].out = h->d_act; chain[1].out_tagged = h->act_tag;
+      chain[2] = TcPhase(); chain[2].mode = TC_MODE_RES; chain[2].W_tiled = w.wd_t; chain[2].N = D; chain[2].K = F;
+      chain[2].x = h->d_act; chain[2].x_tagged = h->act_tag; chain[2].out = h->d_h; chain[2].res = h->d_h; chain[2].out_tagged = h->h_tag;
+      chain[3] = TcPhase(); chain[3].mode = TC_MODE_LOGITS; chain[3].W_tiled = h->lm_head_t; chain[3].N = c.vocab; chain[3].K = D;
+      chain[3].x = h->d_h; chain[3].x_tagged = h->h_tag; chain[3].norm_w = h->norm_w; chain[3].logits = h->logits;
+      ok = ok && gemv_tc_chain_supported(chain, 4);
+    }
+    if (ok) {
+      TcPhase first = qkv_phase(0);
+      VCL_TRY(launch_gemv_tc_chain(&first, 1, cc, st));
+      for (int l = 0; l < c.llm_layers; ++l) {
+        const LlmLayerW& w = h->ll[l];
+        VCL_TRY(launch_decode_attention(h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, 1, H, 128,
+                                        c.max_seq, pos + 1, scale, st));
+        chain[0] = TcPhase(); chain[0].mode = TC_MODE_RES; chain[0].W_tiled = w.wo_t; chain[0].N = D; chain[0].K = D;
+        chain[0].x = h->d_attn; chain[0].out = h->d_h; chain[0].res = h->d_h; chain[0].out_tagged = h->h_tag;
+        chain[1] = TcPhase(); chain[1].mode = TC_MODE_SWIGLU; chain[1].W_tiled = w.wgu_t; chain[1].N = 2 * F; chain[1].K = D;
+        chain[1].x = h->d_h; chain[1].x_tagged = h->h_tag; chain[1].norm_w = w.ln2; chain[1].out = h->d_act; chain[1].out_tagged = h->act_tag;
+        chain[2] = TcPhase(); chain[2].mode = TC_MODE_RES; chain[2].W_tiled = w.wd_t; chain[2].N = D; chain[2].K = F;
+        chain[2].x = h->d_act; chain[2].x_tagged = h->act_tag; chain[2].out = h->d_h; chain[2].res = h->d_h; chain[2].out_tagged = h->h_tag;
+        if (l + 1 < c.llm_layers) {
+          chain[3] = qkv_phase(l + 1); chain[3].x_tagged = h->h_tag;
+        } else {
+          chain[3] = TcPhase(); chain[3].mode = TC_MODE_LOGITS; chain[3].W_tiled = h->lm_head_t; chain[3].N = c.vocab;
+          chain[3].K = D; chain[3].x = h->d_h; chain[3].x_tagged = h->h_tag; chain[3].norm_w = h->norm_w; chain[3].logits = h->logits;
+        }
+        VCL_TRY(launch_gemv_tc_chain(chain, 4, cc, st));
+      }
+      if (logits_out != nullptr && logits_out != h->logits)
+        VCL_CUDA_OK(cudaMemcpyAsync(logits_out, h->logits, (size_t)c.vocab * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (tok_out != nullptr) VCL_TRY(launch_argmax(h->logits, tok_out, out_stride, 1, c.vocab, st));
+      return 0;
+    }
+  }
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlmLayerW& w = h->ll[l];
     if (B >= 2 && B <= 16) {
