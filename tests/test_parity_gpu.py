@@ -262,3 +262,48 @@ def test_336px_mlp2x_variant_end_to_end():
     h1, _, _ = eng.prefill(ids, vf, vs, n_layers=1, want_hidden=True, want_token=False)
     _bar(h1, refb_hs[1], gold_hs[1], "336px llm hidden_states[1]")
     _teacher_forced_check(eng, sd_b, lcfg, ids, vf, 6, "336px / mlp2x_gelu")
+
+
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/video-llava_b200")
+from oracle import vcl_oracle as O
+from _util import make_engine, to_dev, vid_start_of
+cfg = O.LlmCfg(layers=2)
+sd = O.random_llm_state(cfg, seed=5)
+ids = O.make_prompt_ids(cfg, 356, seed=2, batch=1).to("cuda")
+vf = (torch.randn(1, 356, 1024, generator=torch.Generator().manual_seed(11)) * 0.5).half().float().to("cuda")
+eng = make_engine(llm=cfg, max_batch=1, max_seq=480)
+eng.load_llm(to_dev(sd))
+_, _, tok = eng.prefill(ids, vf, vid_start_of(ids, cfg))
+outs = []
+for i in range(3):
+    lg, tok = eng.decode_step(tok, 448 + i, want_logits=True)
+    outs.append(lg.float().cpu().numpy())
+np.save(sys.argv[2], np.stack(outs))
+"""
+
+
+def test_single_clip_decode_variants_agree(tmp_path):
+    """The three single-clip decode implementations must agree on the logits of three consecutive
+    steps at 7B width: one gemv_tc launch per projection (default), the fused phase chains
+    (VCL_DECODE_FUSED=1: same slot order and summation order -> bit-identical), and the CUDA-core
+    GEMV over the row-major weights (VCL_GEMV_LEGACY=1: different summation order -> bf16 noise)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "variant.py"
+    script.write_text(_VARIANT_SCRIPT)
+    res = {}
+    for name, env_add in (("tc", {}), ("fused", {"VCL_DECODE_FUSED": "1"}), ("legacy", {"VCL_GEMV_LEGACY": "1"})):
+        env = dict(os.environ)
+        for k in ("VCL_DECODE_FUSED", "VCL_GEMV_LEGACY", "VCL_MEGAKERNEL"):
+            env.pop(k, None)
+        env.update(env_add)
+        out = tmp_path / f"{name}.npy"
+        subprocess.run([sys.executable, str(script), root, str(out)], check=True, env=env, timeout=600)
+        res[name] = np.load(out)
+    assert np.array_equal(res["tc"], res["fused"])
+    num = np.linalg.norm(res["tc"] - res["legacy"]) / np.linalg.norm(res["legacy"])
+    assert num < 2e-2, num
+    assert (res["tc"].argmax(-1) == res["legacy"].argmax(-1)).mean() >= 2 / 3

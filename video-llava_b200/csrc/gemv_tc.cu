@@ -51,7 +51,8 @@ constexpr int TC_CONSUMERS = TC_CWARPS * 32;
 constexpr int TC_THREADS = TC_CONSUMERS + 32;
 constexpr int TC_KC = 512;                          // k elements per slot
 constexpr int TC_SLOT_BYTES = 16 * TC_KC * 2;       // 16 KB, one bulk copy
-constexpr int TC_MAX_SLOTS = 8;                     // measured optimum (7 B shapes): 6 -> 79 ms, 8 -> 74 ms, 9 -> 79 ms per 31 steps
+constexpr int TC_MAX_SLOTS = 14;                    // barrier array size
+constexpr int TC_DEFAULT_SLOTS = 8;                 // measured optimum (7 B shapes): 6 -> 79 ms, 8 -> 74 ms, 9 -> 79 ms per 31 steps
 constexpr int TC_SMEM_BUDGET = 160 * 1024;          // one CTA per SM; the rest of the SM stays free for the
                                                     // attention kernel's CTAs, which launch early (PDL)
 
@@ -464,12 +465,13 @@ __global__ void gemv_tc_repack_kernel(const bf16* __restrict__ W, bf16* __restri
 
 // shared-memory plan for a chain of phases on `grid` CTAs; returns the slot count (0 = does not fit)
 int plan(const TcPhase* ph, int n, int grid, size_t* smem_bytes, int* x_elems, int* r_cap) {
-  int kmax = 0, rmax = 0;
+  int kmax = 0, rmax = 0, want = TC_DEFAULT_SLOTS;
   for (int i = 0; i < n; ++i) {
     const int n_groups = (ph[i].N + 15) / 16;
     if (n_groups < grid) return 0;                   // every CTA streams at least one row group
     if (ph[i].K % 32 != 0 || ph[i].K > 14336) return 0;
     kmax = ph[i].K > kmax ? ph[i].K : kmax;
+    if (ph[i].ring_slots > want) want = ph[i].ring_slots;
     const int r = ((n_groups + grid - 1) / grid) * 16;
     rmax = r > rmax ? r : rmax;
   }
@@ -477,8 +479,12 @@ int plan(const TcPhase* ph, int n, int grid, size_t* smem_bytes, int* x_elems, i
   static const int env_slots = getenv("VCL_GEMV_TC_SLOTS") ? atoi(getenv("VCL_GEMV_TC_SLOTS")) : 0;
   static const size_t budget = getenv("VCL_GEMV_TC_SMEM_KB") ? (size_t)atoi(getenv("VCL_GEMV_TC_SMEM_KB")) * 1024 : (size_t)TC_SMEM_BUDGET;
   if (fixed + 2 * (size_t)TC_SLOT_BYTES > budget) return 0;
-  int slots = (int)((budget - fixed) / TC_SLOT_BYTES);
-  if (slots > TC_MAX_SLOTS) slots = TC_MAX_SLOTS;
+  // a launch may ask for a deeper ring (the projection after the attention kernel sits resident for
+  // ~7 us with nothing to do but prefetch); the hard limit leaves room for the attention CTAs
+  const size_t limit = want > TC_DEFAULT_SLOTS ? (size_t)212 * 1024 : budget;
+  int slots = (int)((limit - fixed) / TC_SLOT_BYTES);
+  if (want > TC_MAX_SLOTS) want = TC_MAX_SLOTS;
+  if (slots > want) slots = want;
   if (env_slots > 0 && env_slots < slots) slots = env_slots;
   *smem_bytes = (size_t)slots * TC_SLOT_BYTES + fixed;
   *x_elems = kmax; *r_cap = rmax;
@@ -495,6 +501,7 @@ unsigned* g_gen = nullptr;            // generation counter of the tagged hand-o
 TcPhase phase_of(const GemvArgs& g, int mode) {
   TcPhase ph;
   ph.mode = mode; ph.W_tiled = g.W_tiled; ph.N = g.N; ph.K = g.K; ph.x = g.x; ph.norm_w = g.norm_w;
+  ph.ring_slots = g.ring_slots;
   return ph;
 }
 

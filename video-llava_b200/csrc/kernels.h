@@ -126,6 +126,7 @@ struct GemvArgs {
   const bf16* x = nullptr; long long ldx = 0;   // [B, K]
   const bf16* W = nullptr;                      // [N, K]
   const bf16* W_tiled = nullptr;                // optional decode-only tiled copy (gemv_tc.cu), B = 1
+  int ring_slots = 0;                           // gemv_tc: deeper shared-memory ring than the default (0 = default)
   int B = 0, N = 0, K = 0;
   const bf16* norm_w = nullptr; float eps = 0;  // optional fused RMSNorm prologue
 };
@@ -152,6 +153,7 @@ struct TcPhase {
   const bf16* W_tiled = nullptr; int N = 0, K = 0;   // slot-ordered copy of the [N, K] matrix
   const bf16* x = nullptr;                           // [K] input (written by the previous phase / kernel)
   const bf16* norm_w = nullptr;                      // optional fused RMSNorm of x
+  int ring_slots = 0;                                // 0 = default ring depth
   bf16* out = nullptr; const bf16* res = nullptr;    // RES: out[N] (+res); SWIGLU: out[N/2]
   bf16* q_out = nullptr; bf16* kcache = nullptr; bf16* vcache = nullptr;   // QKV (cache base of the layer)
   float* logits = nullptr;                           // LOGITS: [N] bf16-rounded fp32
