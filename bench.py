@@ -377,8 +377,13 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     vals, last = [], None
-    for i in range(max(args.warmup, 0) + args.steps):
-        last = cpu_sample(args.model)
+    n = max(args.warmup, 0) + args.steps
+    # every step is one bounded sample; the samples shrink with the step count so that the whole
+    # run stays within a few minutes (a 1-frame / 1-layer / 1-step sample takes ~20 s on 128 threads)
+    size = dict(t_frames=4, l_layers=2, dec_steps=4) if n <= 2 else \
+        dict(t_frames=2, l_layers=1, dec_steps=2) if n <= 4 else dict(t_frames=1, l_layers=1, dec_steps=1)
+    for i in range(n):
+        last = cpu_sample(args.model, **size)
         if i >= args.warmup:
             vals.append(last["value"])
     v = float(np.mean(vals))
