@@ -237,16 +237,29 @@ def device_weights(model, dev):
     return clip, llm
 
 
+def synthetic_prompt_ids(seed=1, n_pre=63, n_vid=356, n_post=26):
+    """[1] + 63 ids ~ U[3,32000) + <vid_start> + <vid_patch> x 356 + <vid_end>
+    + 26 ids ~ U[3,32000)  ->  S_p = 448 (ids 32000 / 32001 / 32002 are patch / start / end)."""
+    g = torch.Generator().manual_seed(seed)
+    pre = torch.randint(3, 32000, (n_pre,), generator=g)
+    post = torch.randint(3, 32000, (n_post,), generator=g)
+    row = torch.cat([torch.tensor([1]), pre, torch.tensor([32001]), torch.full((n_vid,), 32000), torch.tensor([32002]), post])
+    return row[None].to(torch.int64)
+
+
+def synthetic_frames(clip, t, size=224):
+    return np.random.default_rng(1000 + clip).integers(0, 256, (t, size, size, 3), dtype=np.uint8)
+
+
 def run_vcl(args, rank, world, local_rank):
-    import vcl_native as vn
-    from oracle import vcl_oracle as O   # only for make_prompt_ids / make_frames (synthetic inputs)
+    import vcl_native as vn                 # the product arm never touches oracle/
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: whatever NCCL logs (its version banner included) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     m = MODELS[args.model]
     B = args.clips
@@ -263,10 +276,9 @@ def run_vcl(args, rank, world, local_rank):
     eng.load_llm(llm_sd); del llm_sd
     torch.cuda.empty_cache()
 
-    lcfg = O.LlmCfg(hidden=m["hidden"], inter=m["inter"], heads=m["heads"], layers=m["layers"])
-    ids_h = O.make_prompt_ids(lcfg, 356, seed=1, batch=1).repeat(B, 1).pin_memory()
+    ids_h = synthetic_prompt_ids(seed=1).repeat(B, 1).pin_memory()
     vs_h = torch.full((B,), 64, dtype=torch.int32).pin_memory()
-    frames_h = torch.stack([torch.as_tensor(O.make_frames(rank * B + b, T_FRAMES)) for b in range(B)]).pin_memory()
+    frames_h = torch.stack([torch.as_tensor(synthetic_frames(rank * B + b, T_FRAMES)) for b in range(B)]).pin_memory()
     toks_h = torch.empty(B, N_NEW, dtype=torch.int32).pin_memory()
     frames_d, ids_d, vs_d = frames_h.to(dev), ids_h.to(dev), vs_h.to(dev)
     frames_in = torch.empty_like(frames_d); ids_in = torch.empty_like(ids_d); vs_in = torch.empty_like(vs_d)
