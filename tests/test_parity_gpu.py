@@ -307,3 +307,28 @@ def test_single_clip_decode_variants_agree(tmp_path):
     num = np.linalg.norm(res["tc"] - res["legacy"]) / np.linalg.norm(res["legacy"])
     assert num < 2e-2, num
     assert (res["tc"].argmax(-1) == res["legacy"].argmax(-1)).mean() >= 2 / 3
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("NB", [2, 4])
+def test_decode_small_batch_7b_width(NB):
+    """2..4 clips at 7B width go through the multi-column gemv_tc kernel (activation vectors of all
+    clips in shared memory, one MMA column per clip): per clip it must reproduce the single-clip
+    decode (same weights, same summation order; the caches come from differently tiled prefills)."""
+    cfg = O.LlmCfg(layers=2)
+    sd = O.random_llm_state(cfg, seed=8)
+    ids = O.make_prompt_ids(cfg, 356, seed=6, batch=NB).to(DEV)
+    vf = (torch.randn(NB, 356, 1024, generator=torch.Generator().manual_seed(13)) * 0.5).half().float().to(DEV)
+    eng = make_engine(llm=cfg, max_batch=NB, max_seq=480)
+    eng.load_llm(to_dev(sd))
+    vs = vid_start_of(ids, cfg)
+    _, lg, _ = eng.prefill(ids, vf, vs, want_logits=True)
+    tok = lg.argmax(-1).to(torch.int32)
+    lgb, tokb = eng.decode_step(tok, 448, want_logits=True)
+    lgb2, _ = eng.decode_step(tokb, 449, want_logits=True)
+    for b in range(NB):
+        eng.prefill(ids[b:b + 1], vf[b:b + 1], vs[b:b + 1])
+        l1, t1 = eng.decode_step(tok[b:b + 1].contiguous(), 448, want_logits=True)
+        assert relerr(l1, lgb[b:b + 1]) < 1e-2, (b, relerr(l1, lgb[b:b + 1]))
+        l2, _ = eng.decode_step(tokb[b:b + 1].contiguous(), 449, want_logits=True)
+        assert relerr(l2, lgb2[b:b + 1]) < 1e-2, (b, relerr(l2, lgb2[b:b + 1]))

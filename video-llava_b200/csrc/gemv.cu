@@ -358,7 +358,7 @@ int init_gemv_kernels() {
 
 int launch_gemv_residual(const GemvArgs& g, bf16* out, long long ldo, const bf16* res,
                          long long ldr, cudaStream_t stream) {
-  if (gemv_tc_supported(g)) return launch_gemv_tc_residual(g, out, res, stream);
+  if (gemv_tc_supported(g)) return launch_gemv_tc_residual(g, out, ldo, res, ldr, stream);
   GemvParams p = base_params(g);
   p.out = out; p.ldo = ldo; p.res = res; p.ldr = ldr;
   return launch_mode<MODE_RES>(g.B, p, stream);
@@ -366,7 +366,7 @@ int launch_gemv_residual(const GemvArgs& g, bf16* out, long long ldo, const bf16
 
 int launch_gemv_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t stream) {
   VCL_REQUIRE(g.N % 2 == 0, "gemv swiglu: N must be even (interleaved gate/up rows)");
-  if (gemv_tc_supported(g)) return launch_gemv_tc_swiglu(g, out, stream);
+  if (gemv_tc_supported(g)) return launch_gemv_tc_swiglu(g, out, ldo, stream);
   GemvParams p = base_params(g);
   p.out = out; p.ldo = ldo;
   return launch_mode<MODE_SWIGLU>(g.B, p, stream);
@@ -379,7 +379,7 @@ int launch_gemv_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kc
   VCL_REQUIRE(g.N == 3 * H * 128, "gemv qkv: N=%d != 3*H*128", g.N);
   VCL_REQUIRE(pos >= 0 && pos < s_max, "gemv qkv: position %d outside the cache (%d)", pos, s_max);
   if (gemv_tc_supported(g))
-    return launch_gemv_tc_qkv_rope(g, q_out, kcache, vcache, cos_t, sin_t, H, s_max, pos, stream);
+    return launch_gemv_tc_qkv_rope(g, q_out, ldq, kcache, vcache, cos_t, sin_t, H, s_max, pos, stream);
   GemvParams p = base_params(g);
   p.q_out = q_out; p.ldq = ldq; p.kcache = kcache; p.vcache = vcache;
   p.cos_t = cos_t; p.sin_t = sin_t; p.H = H; p.s_max = s_max; p.pos = pos;
@@ -387,7 +387,7 @@ int launch_gemv_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kc
 }
 
 int launch_gemv_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream) {
-  if (gemv_tc_supported(g)) return launch_gemv_tc_logits(g, logits, stream);
+  if (gemv_tc_supported(g)) return launch_gemv_tc_logits(g, logits, ldl, stream);
   GemvParams p = base_params(g);
   p.logits = logits; p.ldl = ldl;
   return launch_mode<MODE_LOGITS>(g.B, p, stream);

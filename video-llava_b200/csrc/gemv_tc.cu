@@ -61,8 +61,9 @@ constexpr int TC_MAX_PHASES = 4;
 struct TcParams {
   TcPhase ph[TC_MAX_PHASES];        // dependent projections executed back to back by one launch
   int n_phases;
+  int nb;                           // clips per launch (1..4): columns of the MMA B operand
   int n_slots;
-  int x_elems;                      // max K over the phases (activation buffer)
+  int x_elems;                      // max nb * K over the phases (activation buffer)
   int r_cap;                        // max rows one CTA owns in a phase (result buffer)
   float eps;
   const bf16* cos_t; const bf16* sin_t;
@@ -106,12 +107,12 @@ __device__ __forceinline__ long long qkv_row(int v) {
 
 __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // layout: ring[n_slots] | x[x_elems] bf16 | pbuf[2][TC_CWARPS][16] | result[r_cap] fp32 | red | barriers
+  // layout: ring[n_slots] | x[nb][K] bf16 | pbuf[2][TC_CWARPS][16][4] | result[r_cap][4] fp32 | red | barriers
   const int n_slots = p.n_slots;
   bf16* xs = reinterpret_cast<bf16*>(smem + (size_t)n_slots * TC_SLOT_BYTES);
   float* pbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)p.x_elems * 2);
-  float* result = pbuf + 2 * TC_CWARPS * 16;
-  float* red = result + p.r_cap;
+  float* result = pbuf + 2 * TC_CWARPS * 16 * 4;
+  float* red = result + p.r_cap * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16);
   const uint32_t ring0 = smem_u32(smem);
   const uint32_t bar0 = smem_u32(bars);
@@ -185,11 +186,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
     // Activation vector -> shared memory (bf16), RMS-normalised when the layer norm is fused. The
     // norm weights (constants) are parked in the x buffer first, every thread issues its x loads back
     // to back: the dependent latency is one L2 round trip.
+    const int NB = p.nb;
     if (ph.norm_w != nullptr) {
+      for (int b = 0; b < NB; ++b) {
 #pragma unroll
-      for (int u = 0; u < XU; ++u) {
-        const int c = tid + u * TC_CONSUMERS;
-        if (c < nch) *reinterpret_cast<uint4*>(xs + c * 8) = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + c * 8));
+        for (int u = 0; u < XU; ++u) {
+          const int c = tid + u * TC_CONSUMERS;
+          if (c < nch) *reinterpret_cast<uint4*>(xs + (size_t)b * K + c * 8) = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + c * 8));
+        }
       }
     }
     float ss = 0.f;
@@ -203,47 +207,53 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
           red[8] = __uint_as_float(b);
         }
       }
-      uint4 xv[XU];
-#pragma unroll
-      for (int u = 0; u < XU; ++u) {
-        const int c = tid + u * TC_CONSUMERS;
-        xv[u] = (c < nch) ? ld_cg_v4(ph.x + c * 8) : make_uint4(0, 0, 0, 0);
-      }
-      if (ph.norm_w != nullptr) {
-#pragma unroll
-        for (int u = 0; u < XU; ++u) {
-          const uint4 v = xv[u];
-          const float f0 = bf16lo(v.x), f1 = bf16hi(v.x), f2 = bf16lo(v.y), f3 = bf16hi(v.y);
-          const float f4 = bf16lo(v.z), f5 = bf16hi(v.z), f6 = bf16lo(v.w), f7 = bf16hi(v.w);
-          ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) red[warp] = ss;
-        cbar();
-        float tot = 0.f;
-#pragma unroll
-        for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
-        const float rstd = rsqrtf(tot / (float)K + p.eps);
+      for (int b = 0; b < NB; ++b) {                  // one clip after the other (one L2 round trip each)
+        bf16* xb = xs + (size_t)b * K;
+        const bf16* xg = ph.x + (long long)b * ph.ldx;
+        uint4 xv[XU];
 #pragma unroll
         for (int u = 0; u < XU; ++u) {
           const int c = tid + u * TC_CONSUMERS;
-          if (c < nch) {
+          xv[u] = (c < nch) ? ld_cg_v4(xg + c * 8) : make_uint4(0, 0, 0, 0);
+        }
+        if (ph.norm_w != nullptr) {
+          ss = 0.f;
+#pragma unroll
+          for (int u = 0; u < XU; ++u) {
             const uint4 v = xv[u];
-            const uint4 gw = *reinterpret_cast<const uint4*>(xs + c * 8);
-            uint4 o;
-            // w * bf16(x * rstd), the product rounded to bf16 again (LlamaRMSNorm)
-            o.x = bf16x2_mul(gw.x, pack_bf16x2(bf16lo(v.x) * rstd, bf16hi(v.x) * rstd));
-            o.y = bf16x2_mul(gw.y, pack_bf16x2(bf16lo(v.y) * rstd, bf16hi(v.y) * rstd));
-            o.z = bf16x2_mul(gw.z, pack_bf16x2(bf16lo(v.z) * rstd, bf16hi(v.z) * rstd));
-            o.w = bf16x2_mul(gw.w, pack_bf16x2(bf16lo(v.w) * rstd, bf16hi(v.w) * rstd));
-            *reinterpret_cast<uint4*>(xs + c * 8) = o;
+            const float f0 = bf16lo(v.x), f1 = bf16hi(v.x), f2 = bf16lo(v.y), f3 = bf16hi(v.y);
+            const float f4 = bf16lo(v.z), f5 = bf16hi(v.z), f6 = bf16lo(v.w), f7 = bf16hi(v.w);
+            ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
           }
-        }
-      } else {
+          ss = warp_sum(ss);
+          if (b > 0) cbar();                          // red[] of the previous clip has been read
+          if (lane == 0) red[warp] = ss;
+          cbar();
+          float tot = 0.f;
 #pragma unroll
-        for (int u = 0; u < XU; ++u) {
-          const int c = tid + u * TC_CONSUMERS;
-          if (c < nch) *reinterpret_cast<uint4*>(xs + c * 8) = xv[u];
+          for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
+          const float rstd = rsqrtf(tot / (float)K + p.eps);
+#pragma unroll
+          for (int u = 0; u < XU; ++u) {
+            const int c = tid + u * TC_CONSUMERS;
+            if (c < nch) {
+              const uint4 v = xv[u];
+              const uint4 gw = *reinterpret_cast<const uint4*>(xb + c * 8);
+              uint4 o;
+              // w * bf16(x * rstd), the product rounded to bf16 again (LlamaRMSNorm)
+              o.x = bf16x2_mul(gw.x, pack_bf16x2(bf16lo(v.x) * rstd, bf16hi(v.x) * rstd));
+              o.y = bf16x2_mul(gw.y, pack_bf16x2(bf16lo(v.y) * rstd, bf16hi(v.y) * rstd));
+              o.z = bf16x2_mul(gw.z, pack_bf16x2(bf16lo(v.z) * rstd, bf16hi(v.z) * rstd));
+              o.w = bf16x2_mul(gw.w, pack_bf16x2(bf16lo(v.w) * rstd, bf16hi(v.w) * rstd));
+              *reinterpret_cast<uint4*>(xb + c * 8) = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < XU; ++u) {
+            const int c = tid + u * TC_CONSUMERS;
+            if (c < nch) *reinterpret_cast<uint4*>(xb + c * 8) = xv[u];
+          }
         }
       }
       cbar();
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
             const uint4 wa = *reinterpret_cast<const uint4*>(base + kb * 1024 + lane * 16);        // row g
             const uint4 wb = *reinterpret_cast<const uint4*>(base + kb * 1024 + 512 + lane * 16);  // row g+8
             uint4 xq = make_uint4(0, 0, 0, 0);
-            if (g == 0) xq = *reinterpret_cast<const uint4*>(xs + kc * TC_KC + kb * 32 + q * 8);
+            if (g < NB) xq = *reinterpret_cast<const uint4*>(xs + (size_t)g * K + kc * TC_KC + kb * 32 + q * 8);   // column g = clip g
             tc_mma(c, wa.x, wb.x, wa.y, wb.y, xq.x, xq.y);
             tc_mma(c, wa.z, wb.z, wa.w, wb.w, xq.z, xq.w);
           }
@@ -352,17 +362,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
       }
       // the 8 per-warp partials of this row group meet in shared memory (double-buffered: the barrier
       // of the next group orders the reads below before the buffer is written again)
-      float* pb = pbuf + (grp & 1) * TC_CWARPS * 16;
-      if (q == 0) {                                   // column 0: rows g (c[0]) and g+8 (c[2])
-        pb[warp * 16 + g] = c[0];
-        pb[warp * 16 + g + 8] = c[2];
+      float* pb = pbuf + (grp & 1) * TC_CWARPS * 16 * 4;
+      if (q < 2) {                                    // columns (clips) 2q, 2q+1: rows g (c[0], c[1]) and g+8 (c[2], c[3])
+        *reinterpret_cast<float2*>(pb + (warp * 16 + g) * 4 + 2 * q) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(pb + (warp * 16 + g + 8) * 4 + 2 * q) = make_float2(c[2], c[3]);
       }
       cbar();
-      if (tid < 16) {
+      if (tid < 64) {                                 // (row, clip) = (tid / 4, tid % 4)
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < TC_CWARPS; ++w) v += pb[w * 16 + tid];
-        result[grp * 16 + tid] = v;
+        for (int w = 0; w < TC_CWARPS; ++w) v += pb[w * 64 + tid];
+        result[grp * 64 + tid] = v;
       }
     }
     cbar();
@@ -371,38 +381,40 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
     // ---------------- fused epilogue ----------------
     const bool pairs = (mode == TC_MODE_SWIGLU || mode == TC_MODE_QKV);
     const int R = ng * 16;
-    const int n_items = pairs ? R / 2 : R;
+    const int n_items = (pairs ? R / 2 : R) * NB;     // item = (row or row pair, clip), clip fastest for NB > 1
     const unsigned tag_out = (p.n_phases > 1 ? __float_as_uint(red[8]) * 8u : 0u) + (unsigned)i + 1u;
     for (int it0 = 0; it0 < n_items; it0 += TC_CONSUMERS) {       // uniform trip count: the warps stay converged
       const int it = it0 + tid;
-      const int rr = pairs ? 2 * it : it;
+      const int b = (NB == 1) ? 0 : it % NB;
+      const int iu = (NB == 1) ? it : it / NB;
+      const int rr = pairs ? 2 * iu : iu;
       const int vrow = row0 + rr;
       const bool valid = it < n_items && vrow < N;
       float y = 0.f;                                 // RES / SWIGLU: the output value of this item
       if (valid) {
-        const float v0 = result[rr];
-        const float v1 = pairs ? result[rr + 1] : 0.f;
+        const float v0 = result[rr * 4 + b];
+        const float v1 = pairs ? result[(rr + 1) * 4 + b] : 0.f;
         if (mode == TC_MODE_RES) {
           y = bf16r(v0);
           if (ph.res != nullptr) {                    // may have been written by an earlier phase: read through L2
             unsigned short rv;
-            asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(rv) : "l"(ph.res + vrow) : "memory");
+            asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(rv) : "l"(ph.res + (long long)b * ph.ldr + vrow) : "memory");
             y += __uint_as_float((uint32_t)rv << 16);
           }
-          ph.out[vrow] = __float2bfloat16_rn(y);
+          ph.out[(long long)b * ph.ldo + vrow] = __float2bfloat16_rn(y);
         } else if (mode == TC_MODE_LOGITS) {
-          ph.logits[vrow] = bf16r(v0);
+          ph.logits[(long long)b * ph.ldl + vrow] = bf16r(v0);
         } else if (mode == TC_MODE_SWIGLU) {
           const float gt = bf16r(v0);
           const float sg = bf16r(__fdividef(gt, 1.0f + __expf(-gt)));
           y = sg * bf16r(v1);
-          ph.out[vrow >> 1] = __float2bfloat16_rn(y);
+          ph.out[(long long)b * ph.ldo + (vrow >> 1)] = __float2bfloat16_rn(y);
         } else {  // TC_MODE_QKV: vrow = (which*H + head)*128 + 2*d
           const int hr = vrow >> 7;
           const int which = hr / p.H, head = hr - which * p.H;
           const int d = (vrow & 127) >> 1;
           const float lo = bf16r(v0), hi = bf16r(v1);
-          const long long coff = ((long long)head * p.s_max + p.pos) * 128;
+          const long long coff = (((long long)b * p.H + head) * p.s_max + p.pos) * 128;
           if (which == 2) {
             ph.vcache[coff + d] = __float2bfloat16_rn(lo);
             ph.vcache[coff + d + 64] = __float2bfloat16_rn(hi);
@@ -412,8 +424,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
             const float olo = bf16r(lo * cs) + bf16r(-hi * sn);
             const float ohi = bf16r(hi * cs) + bf16r(lo * sn);
             if (which == 0) {
-              ph.q_out[head * 128 + d] = __float2bfloat16_rn(olo);
-              ph.q_out[head * 128 + d + 64] = __float2bfloat16_rn(ohi);
+              ph.q_out[(long long)b * ph.ldq + head * 128 + d] = __float2bfloat16_rn(olo);
+              ph.q_out[(long long)b * ph.ldq + head * 128 + d + 64] = __float2bfloat16_rn(ohi);
             } else {
               ph.kcache[coff + d] = __float2bfloat16_rn(olo);
               ph.kcache[coff + d + 64] = __float2bfloat16_rn(ohi);
@@ -464,7 +476,7 @@ __global__ void gemv_tc_repack_kernel(const bf16* __restrict__ W, bf16* __restri
 }
 
 // shared-memory plan for a chain of phases on `grid` CTAs; returns the slot count (0 = does not fit)
-int plan(const TcPhase* ph, int n, int grid, size_t* smem_bytes, int* x_elems, int* r_cap) {
+int plan(const TcPhase* ph, int n, int nb, int grid, size_t* smem_bytes, int* x_elems, int* r_cap) {
   int kmax = 0, rmax = 0, want = TC_DEFAULT_SLOTS;
   for (int i = 0; i < n; ++i) {
     const int n_groups = (ph[i].N + 15) / 16;
@@ -475,19 +487,19 @@ int plan(const TcPhase* ph, int n, int grid, size_t* smem_bytes, int* x_elems, i
     const int r = ((n_groups + grid - 1) / grid) * 16;
     rmax = r > rmax ? r : rmax;
   }
-  const size_t fixed = (size_t)kmax * 2 + (size_t)(2 * TC_CWARPS * 16 + rmax) * 4 + 16 * 4 + 2 * TC_MAX_SLOTS * 8 + 128;
+  const size_t fixed = (size_t)nb * kmax * 2 + (size_t)(2 * TC_CWARPS * 16 + rmax) * 4 * 4 + 16 * 4 + 2 * TC_MAX_SLOTS * 8 + 128;
   static const int env_slots = getenv("VCL_GEMV_TC_SLOTS") ? atoi(getenv("VCL_GEMV_TC_SLOTS")) : 0;
   static const size_t budget = getenv("VCL_GEMV_TC_SMEM_KB") ? (size_t)atoi(getenv("VCL_GEMV_TC_SMEM_KB")) * 1024 : (size_t)TC_SMEM_BUDGET;
-  if (fixed + 2 * (size_t)TC_SLOT_BYTES > budget) return 0;
+  if (fixed + 4 * (size_t)TC_SLOT_BYTES > (nb > 1 ? (size_t)212 * 1024 : budget)) return 0;
   // a launch may ask for a deeper ring (the projection after the attention kernel sits resident for
   // ~7 us with nothing to do but prefetch); the hard limit leaves room for the attention CTAs
-  const size_t limit = want > TC_DEFAULT_SLOTS ? (size_t)212 * 1024 : budget;
+  const size_t limit = (want > TC_DEFAULT_SLOTS || nb > 1) ? (size_t)212 * 1024 : budget;   // several clips: x takes the room
   int slots = (int)((limit - fixed) / TC_SLOT_BYTES);
   if (want > TC_MAX_SLOTS) want = TC_MAX_SLOTS;
   if (slots > want) slots = want;
   if (env_slots > 0 && env_slots < slots) slots = env_slots;
   *smem_bytes = (size_t)slots * TC_SLOT_BYTES + fixed;
-  *x_elems = kmax; *r_cap = rmax;
+  *x_elems = nb * kmax; *r_cap = rmax;
   return slots;
 }
 
@@ -501,7 +513,7 @@ unsigned* g_gen = nullptr;            // generation counter of the tagged hand-o
 TcPhase phase_of(const GemvArgs& g, int mode) {
   TcPhase ph;
   ph.mode = mode; ph.W_tiled = g.W_tiled; ph.N = g.N; ph.K = g.K; ph.x = g.x; ph.norm_w = g.norm_w;
-  ph.ring_slots = g.ring_slots;
+  ph.ring_slots = g.ring_slots; ph.B = g.B; ph.ldx = g.ldx;
   return ph;
 }
 
@@ -515,8 +527,11 @@ bool gemv_tc_chain_supported(const TcPhase* ph, int n) {
     if (((uintptr_t)ph[i].x % 16) != 0 || ((uintptr_t)ph[i].W_tiled % 16) != 0) return false;
     if ((ph[i].mode == TC_MODE_SWIGLU || ph[i].mode == TC_MODE_QKV) && ph[i].N % 2 != 0) return false;
   }
+  const int nb = ph[0].B;
+  if (nb < 1 || nb > 4 || (nb > 1 && n > 1)) return false;          // the phase hand-off is single-clip
+  for (int i = 1; i < n; ++i) if (ph[i].B != nb) return false;
   size_t smem = 0; int xe = 0, rc = 0;
-  return plan(ph, n, device_num_sms(), &smem, &xe, &rc) >= 2;
+  return plan(ph, n, nb, device_num_sms(), &smem, &xe, &rc) >= 4;
 }
 
 int launch_gemv_tc_chain(const TcPhase* ph, int n, const TcChainCommon& c, cudaStream_t stream) {
@@ -526,8 +541,10 @@ int launch_gemv_tc_chain(const TcPhase* ph, int n, const TcChainCommon& c, cudaS
   for (int i = 0; i < n; ++i) p.ph[i] = ph[i];
   p.n_phases = n; p.eps = c.eps; p.cos_t = c.cos_t; p.sin_t = c.sin_t; p.H = c.H; p.s_max = c.s_max; p.pos = c.pos;
   size_t smem = 0;
-  p.n_slots = plan(ph, n, grid, &smem, &p.x_elems, &p.r_cap);
-  VCL_REQUIRE(p.n_slots >= 2, "gemv_tc: the phases (first N=%d K=%d) do not fit the shared-memory plan", ph[0].N, ph[0].K);
+  p.nb = ph[0].B;
+  VCL_REQUIRE(p.nb >= 1 && p.nb <= 4 && (p.nb == 1 || n == 1), "gemv_tc: %d clips x %d phases not supported", p.nb, n);
+  p.n_slots = plan(ph, n, p.nb, grid, &smem, &p.x_elems, &p.r_cap);
+  VCL_REQUIRE(p.n_slots >= 4, "gemv_tc: the phases (first N=%d K=%d) do not fit the shared-memory plan", ph[0].N, ph[0].K);
   if (g_gen == nullptr) {
     const unsigned one = 1;                          // generation 0 would match zero-initialised buffers
     VCL_CUDA_OK(cudaMalloc(&g_gen, sizeof(unsigned)));
@@ -589,7 +606,7 @@ int init_gemv_tc_kernels() {
 
 // B = 1, 16-byte aligned operands, K a multiple of 32 and a shared-memory plan that fits
 bool gemv_tc_supported(const GemvArgs& g) {
-  if (g.B != 1) return false;
+  if (g.B < 1 || g.B > 4 || g.ldx % 8 != 0) return false;
   const TcPhase ph = phase_of(g, TC_MODE_RES);
   return gemv_tc_chain_supported(&ph, 1);
 }
@@ -604,32 +621,33 @@ int launch_gemv_tc_repack(const bf16* W, bf16* dst, int N, int K, bool qkv_pairs
   return 0;
 }
 
-int launch_gemv_tc_residual(const GemvArgs& g, bf16* out, const bf16* res, cudaStream_t stream) {
+int launch_gemv_tc_residual(const GemvArgs& g, bf16* out, long long ldo, const bf16* res, long long ldr,
+                            cudaStream_t stream) {
   TcPhase ph = phase_of(g, TC_MODE_RES);
-  ph.out = out; ph.res = res;
+  ph.out = out; ph.ldo = ldo; ph.res = res; ph.ldr = ldr;
   TcChainCommon c; c.eps = g.eps;
   return launch_gemv_tc_chain(&ph, 1, c, stream);
 }
 
-int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, cudaStream_t stream) {
+int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t stream) {
   VCL_REQUIRE(g.N % 2 == 0, "gemv swiglu: N must be even (interleaved gate/up rows)");
   TcPhase ph = phase_of(g, TC_MODE_SWIGLU);
-  ph.out = out;
+  ph.out = out; ph.ldo = ldo;
   TcChainCommon c; c.eps = g.eps;
   return launch_gemv_tc_chain(&ph, 1, c, stream);
 }
 
-int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, bf16* kcache, bf16* vcache, const bf16* cos_t,
-                            const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream) {
+int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
+                            const bf16* cos_t, const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream) {
   TcPhase ph = phase_of(g, TC_MODE_QKV);
-  ph.q_out = q_out; ph.kcache = kcache; ph.vcache = vcache;
+  ph.q_out = q_out; ph.ldq = ldq; ph.kcache = kcache; ph.vcache = vcache;
   TcChainCommon c; c.eps = g.eps; c.cos_t = cos_t; c.sin_t = sin_t; c.H = H; c.s_max = s_max; c.pos = pos;
   return launch_gemv_tc_chain(&ph, 1, c, stream);
 }
 
-int launch_gemv_tc_logits(const GemvArgs& g, float* logits, cudaStream_t stream) {
+int launch_gemv_tc_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream) {
   TcPhase ph = phase_of(g, TC_MODE_LOGITS);
-  ph.logits = logits;
+  ph.logits = logits; ph.ldl = ldl;
   TcChainCommon c; c.eps = g.eps;
   return launch_gemv_tc_chain(&ph, 1, c, stream);
 }

@@ -141,7 +141,7 @@ int launch_gemv_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kc
                          int pos, cudaStream_t stream);
 int init_gemv_kernels();
 
-// ---- gemv_tc.cu : B = 1 variant (bulk-copy ring + mma.sync, two kernels co-resident per SM) ------
+// ---- gemv_tc.cu : 1..4 clips (bulk-copy ring over a slot-ordered weight copy + mma.sync) ---------
 // The launch_gemv_* entry points above route to these when gemv_tc_supported(g).
 int init_gemv_tc_kernels();
 // One launch can run up to 4 DEPENDENT projections back to back (o_proj -> gate/up -> down -> next
@@ -151,12 +151,15 @@ enum { TC_MODE_RES = 0, TC_MODE_SWIGLU = 1, TC_MODE_QKV = 2, TC_MODE_LOGITS = 3 
 struct TcPhase {
   int mode = TC_MODE_RES;
   const bf16* W_tiled = nullptr; int N = 0, K = 0;   // slot-ordered copy of the [N, K] matrix
-  const bf16* x = nullptr;                           // [K] input (written by the previous phase / kernel)
+  const bf16* x = nullptr; long long ldx = 0;        // [B][ldx] input (written by the previous phase / kernel)
+  int B = 1;                                         // clips (1..4; chains of several phases: 1)
   const bf16* norm_w = nullptr;                      // optional fused RMSNorm of x
   int ring_slots = 0;                                // 0 = default ring depth
-  bf16* out = nullptr; const bf16* res = nullptr;    // RES: out[N] (+res); SWIGLU: out[N/2]
-  bf16* q_out = nullptr; bf16* kcache = nullptr; bf16* vcache = nullptr;   // QKV (cache base of the layer)
-  float* logits = nullptr;                           // LOGITS: [N] bf16-rounded fp32
+  bf16* out = nullptr; long long ldo = 0;            // RES: out[B][N] (+res); SWIGLU: out[B][N/2]
+  const bf16* res = nullptr; long long ldr = 0;
+  bf16* q_out = nullptr; long long ldq = 0;          // QKV: q [B][ldq], cache base of the layer [B][H][S][128]
+  bf16* kcache = nullptr; bf16* vcache = nullptr;
+  float* logits = nullptr; long long ldl = 0;        // LOGITS: [B][ldl] bf16-rounded fp32
   // hand-off between the phases of one launch: the same vector as `out` / `x`, as 8-byte units
   // {bf16, bf16, u32 generation} (see gemv_tc.cu); x_tagged is read by every phase but the first
   unsigned long long* out_tagged = nullptr;
@@ -173,11 +176,12 @@ bool gemv_tc_supported(const GemvArgs& g);
 size_t gemv_tc_tiled_elems(int N, int K);     // elements of the tiled copy of an [N, K] matrix
 // qkv_pairs: rows are taken in the order of the fused q/k/v kernel (RoPE pairs adjacent)
 int launch_gemv_tc_repack(const bf16* W, bf16* dst, int N, int K, bool qkv_pairs, cudaStream_t stream);
-int launch_gemv_tc_residual(const GemvArgs& g, bf16* out, const bf16* res, cudaStream_t stream);
-int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, cudaStream_t stream);
-int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, bf16* kcache, bf16* vcache, const bf16* cos_t,
-                            const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream);
-int launch_gemv_tc_logits(const GemvArgs& g, float* logits, cudaStream_t stream);
+int launch_gemv_tc_residual(const GemvArgs& g, bf16* out, long long ldo, const bf16* res, long long ldr,
+                            cudaStream_t stream);
+int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t stream);
+int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
+                            const bf16* cos_t, const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream);
+int launch_gemv_tc_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
 // logits (bf16-rounded, stored fp32) [B, N]
 int launch_gemv_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
 

@@ -460,11 +460,26 @@ int clip_forward(vcl_handle* h, const void* pixels, int fmt, int n_frames, int n
 bf16* kc_layer(vcl_handle* h, int l) { return h->kcache + (size_t)l * h->cache_layer_elems(); }
 bf16* vc_layer(vcl_handle* h, int l) { return h->vcache + (size_t)l * h->cache_layer_elems(); }
 
+// 2..4 clips can take the single-clip kernel family (gemv_tc, activation vectors of all clips in shared
+// memory) when every projection of the model fits its shared-memory plan; 5..16 clips use gemv_mma
+static bool tc_small_batch(vcl_handle* h, int B) {
+  if (B < 2 || B > 4 || h->lm_head_t == nullptr || h->ll.empty()) return false;
+  const vcl_config& c = h->cfg;
+  const int D = c.llm_hidden, F = c.llm_inter;
+  const int shapes[5][2] = {{3 * D, D}, {D, D}, {2 * F, D}, {D, F}, {c.vocab, D}};
+  for (const auto& nk : shapes) {
+    GemvArgs g;
+    g.x = h->d_h; g.ldx = nk[1]; g.W = h->lm_head; g.W_tiled = h->lm_head_t; g.B = B; g.N = nk[0]; g.K = nk[1];
+    if (!gemv_tc_supported(g)) return false;
+  }
+  return true;
+}
+
 // final RMSNorm + lm_head on rows x[b*ldx .. ] (b < B), arg-max
 int lm_head_argmax(vcl_handle* h, const bf16* x, long long ldx, int B, float* logits_out,
                    int32_t* tok_out, long long tok_stride, cudaStream_t st) {
   const vcl_config& c = h->cfg;
-  if (B >= 2) {
+  if (B >= 2 && !tc_small_batch(h, B)) {
     // small batches: normalise the B rows once, then the mma.sync weight-streaming kernel
     for (int b0 = 0; b0 < B; b0 += 16) {
       const int nb = B - b0 < 16 ? B - b0 : 16;
@@ -627,9 +642,10 @@ int llm_decode_step(vcl_handle* h, const int32_t* tok_in, long long in_stride, i
       return 0;
     }
   }
+  const bool tc_small = tc_small_batch(h, B);
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlmLayerW& w = h->ll[l];
-    if (B >= 2 && B <= 16) {
+    if (B >= 2 && B <= 16 && !tc_small) {
       GemvArgs g;
       VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln1, B, D, c.rms_eps, st));
       g.x = h->d_x; g.ldx = D; g.W = w.wqkv; g.B = B; g.N = 3 * D; g.K = D;
@@ -884,7 +900,7 @@ int vcl_op_gemv(const void* x, const void* W, void* out, const void* res, const 
   // single-row case: exercise the tiled-copy kernel the decode loop uses (the copy is built here,
   // on the fly - this entry point is a test hook, not a hot path)
   bf16* tiled = nullptr;
-  if (B == 1 && K % 32 == 0 && N >= 16 && getenv("VCL_GEMV_LEGACY") == nullptr) {
+  if (B <= 4 && K % 32 == 0 && N >= 16 && getenv("VCL_GEMV_LEGACY") == nullptr) {
     VCL_CUDA_OK(cudaMalloc(&tiled, gemv_tc_tiled_elems(N, K) * sizeof(bf16)));
     const int rc = launch_gemv_tc_repack(g.W, tiled, N, K, false, as_stream(stream));
     if (rc != 0) { cudaFree(tiled); return rc; }
