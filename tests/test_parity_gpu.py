@@ -269,7 +269,7 @@ import sys, numpy as np, torch
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/video-llava_b200")
 from oracle import vcl_oracle as O
 from _util import make_engine, to_dev, vid_start_of
-cfg = O.LlmCfg(layers=2)
+cfg = O.LlmCfg(hidden=2560, inter=6912, heads=20, layers=2)   # smallest width whose every projection takes the ring kernel
 sd = O.random_llm_state(cfg, seed=5)
 ids = O.make_prompt_ids(cfg, 356, seed=2, batch=1).to("cuda")
 vf = (torch.randn(1, 356, 1024, generator=torch.Generator().manual_seed(11)) * 0.5).half().float().to("cuda")
@@ -286,7 +286,7 @@ np.save(sys.argv[2], np.stack(outs))
 
 def test_single_clip_decode_variants_agree(tmp_path):
     """The three single-clip decode implementations must agree on the logits of three consecutive
-    steps at 7B width: one gemv_tc launch per projection (default), the fused phase chains
+    steps (width 2560, the smallest that takes the ring kernel everywhere): one gemv_tc launch per projection (default), the fused phase chains
     (VCL_DECODE_FUSED=1: same slot order and summation order -> bit-identical), and the CUDA-core
     GEMV over the row-major weights (VCL_GEMV_LEGACY=1: different summation order -> bf16 noise)."""
     import subprocess
@@ -311,11 +311,11 @@ def test_single_clip_decode_variants_agree(tmp_path):
 
 @torch.no_grad()
 @pytest.mark.parametrize("NB", [2, 4])
-def test_decode_small_batch_7b_width(NB):
-    """2..4 clips at 7B width go through the multi-column gemv_tc kernel (activation vectors of all
+def test_decode_small_batch_ring_kernel(NB):
+    """2..4 clips (width 2560) go through the multi-column gemv_tc kernel (activation vectors of all
     clips in shared memory, one MMA column per clip): per clip it must reproduce the single-clip
     decode (same weights, same summation order; the caches come from differently tiled prefills)."""
-    cfg = O.LlmCfg(layers=2)
+    cfg = O.LlmCfg(hidden=2560, inter=6912, heads=20, layers=2)   # every projection >= 148 row groups: ring kernel
     sd = O.random_llm_state(cfg, seed=8)
     ids = O.make_prompt_ids(cfg, 356, seed=6, batch=NB).to(DEV)
     vf = (torch.randn(NB, 356, 1024, generator=torch.Generator().manual_seed(13)) * 0.5).half().float().to(DEV)
