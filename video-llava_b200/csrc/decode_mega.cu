@@ -571,7 +571,7 @@ int launch_decode_mega(const MegaParams& p, int B, cudaStream_t stream) {
   const bool tracing = trace_path != nullptr && cap == cudaStreamCaptureStatusNone;
   const size_t trace_n = (size_t)device_num_sms() * (p.L * 6 + 1) * 8;
   MegaParams q = p;
-  static const int l2_slots = getenv("VCL_MEGA_L2_SLOTS") ? atoi(getenv("VCL_MEGA_L2_SLOTS")) : 12;
+  static const int l2_slots = getenv("VCL_MEGA_L2_SLOTS") ? atoi(getenv("VCL_MEGA_L2_SLOTS")) : 0;   // measured: any L2 look-ahead is slower (86 -> 140 ms)
   q.l2_slots = l2_slots;
   if (tracing) {
     if (trace_buf == nullptr) VCL_CUDA_OK(cudaMalloc(&trace_buf, trace_n * sizeof(unsigned long long)));
