@@ -87,6 +87,19 @@ def test_prompt_template_and_stop_criterion(built):
     assert crit2(torch.tensor([[1, 7, 8, 9, 10]])) is True           # substring of the decoded text ("jk")
 
 
+def test_video_feature_cache_lru(built):
+    """The optional per-video cache of pooled features (multi-turn chats)."""
+    from video_chatgpt.inference import VideoFeatureCache
+    c = VideoFeatureCache(capacity=2)
+    assert c.get("a") is None and c.misses == 1
+    c.put("a", torch.zeros(1)); c.put("b", torch.ones(1))
+    assert c.get("a") is not None and c.hits == 1              # "a" becomes the most recent
+    c.put("c", torch.full((1,), 2.0))                           # evicts "b", the least recently used
+    assert len(c) == 2 and c.get("b") is None and c.get("a") is not None and c.get("c") is not None
+    with pytest.raises(ValueError):
+        VideoFeatureCache(capacity=0)
+
+
 def test_video_span_validation_errors(built):
     from oracle import vcl_oracle as O
     from video_chatgpt.model import VideoChatGPTConfig, VideoChatGPTLlamaForCausalLM
