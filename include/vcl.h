@@ -123,6 +123,16 @@ int vcl_llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats,
                     const int32_t* vid_start, int B, int S, int n_layers, void* hidden_out,
                     float* logits_out, int32_t* next_tok, void* stream);
 
+/* Continue a cached sequence: S more token ids per clip (text only, no video span) take positions
+ * [start_pos, start_pos + S) and attend to everything already in the KV cache. This is the building
+ * block for multi-turn conversations about one video: the reference re-runs the vision tower and the
+ * whole prompt on every turn (video_chatgpt/chat.py:137-154, inference.py:86-112); with the cache of
+ * the previous turn only the new question is prefilled. Outputs as in vcl_llm_prefill (hidden_out
+ * [B,S,D] of the new positions; logits / next token at the last new position). start_pos must be the
+ * number of positions the cache of every clip already holds (> 0). */
+int vcl_llm_prefill_append(vcl_handle* h, const int64_t* ids, int B, int S, int start_pos, void* hidden_out,
+                           float* logits_out, int32_t* next_tok, void* stream);
+
 /* One cached decoding step (the `input_ids.shape[1] == 1` branch, model/video_chatgpt.py:103,
  * 253-257): tok_in [B] int32 are fed at position `pos` (= tokens already in the cache).
  * logits_out / tok_out as above. Used for teacher-forced parity checks. */

@@ -332,3 +332,34 @@ def test_decode_small_batch_ring_kernel(NB):
         assert relerr(l1, lgb[b:b + 1]) < 1e-2, (b, relerr(l1, lgb[b:b + 1]))
         l2, _ = eng.decode_step(tokb[b:b + 1].contiguous(), 449, want_logits=True)
         assert relerr(l2, lgb2[b:b + 1]) < 1e-2, (b, relerr(l2, lgb2[b:b + 1]))
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("B,n_new", [(1, 24), (2, 70)])
+def test_prefill_append_matches_full_prefill(B, n_new):
+    """Multi-turn reuse of the KV cache (vcl_llm_prefill_append): prefilling a prompt and then appending
+    n_new more tokens must give the hidden states / logits of prefilling everything at once (same
+    arithmetic; the GEMM tiles differ, hence bf16 noise), and decoding continues identically."""
+    cfg = O.LlmCfg(hidden=512, inter=1024, heads=4, layers=2)
+    sd = O.random_llm_state(cfg, seed=31)
+    ids = O.make_prompt_ids(cfg, 356, seed=9, batch=B)
+    extra = torch.randint(3, 32000, (B, n_new), generator=torch.Generator().manual_seed(5))
+    full = torch.cat([ids, extra], 1).to(DEV)
+    ids = ids.to(DEV)
+    vf = (torch.randn(B, 356, 1024, generator=torch.Generator().manual_seed(14)) * 0.5).half().float().to(DEV)
+    eng = make_engine(llm=cfg, max_batch=B, max_seq=448 + n_new + 8)
+    eng.load_llm(to_dev(sd))
+    vs = vid_start_of(ids, cfg)
+    S0, S1 = ids.shape[1], full.shape[1]
+    h_full, lg_full, tok_full = eng.prefill(full, vf, vs, want_hidden=True, want_logits=True)
+    lg_full2, _ = eng.decode_step(tok_full, S1, want_logits=True)
+    eng.prefill(ids, vf, vs)
+    h_new, lg_new, tok_new = eng.prefill_append(full[:, S0:], S0, want_hidden=True, want_logits=True)
+    assert relerr(h_new, h_full[:, S0:]) < 1e-2, relerr(h_new, h_full[:, S0:])
+    assert relerr(lg_new, lg_full) < 1e-2, relerr(lg_new, lg_full)
+    lg_new2, _ = eng.decode_step(tok_full, S1, want_logits=True)     # teacher-forced with the same token
+    assert relerr(lg_new2, lg_full2) < 1e-2, relerr(lg_new2, lg_full2)
+    with pytest.raises(vn.VclError):
+        eng.prefill_append(full[:, S0:], 0)                           # a continuation needs a cache
+    with pytest.raises(vn.VclError):
+        eng.prefill_append(full[:, S0:], 448 + 9)                     # would run past max_seq

@@ -82,18 +82,20 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
 
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = a.S;
+  const int S = a.S;                                  // queries
+  const int S_kv = a.S_kv > 0 ? a.S_kv : a.S;         // keys (a continued prefill attends to the cache too)
+  const int q_off = a.q_off;                          // absolute position of query 0 (causal mask)
   const int q0 = qt * 64;
   const bf16* qg = a.q + (long long)b * a.q_sb + (long long)h * a.q_sh;
   const bf16* kg = a.k + (long long)b * a.k_sb + (long long)h * a.k_sh;
   const bf16* vg = a.v + (long long)b * a.v_sb + (long long)h * a.v_sh;
 
-  const int n_tiles_all = (S + 63) / 64;
-  const int n_tiles = CAUSAL ? min(n_tiles_all, qt + 1) : n_tiles_all;
+  const int n_tiles_all = (S_kv + 63) / 64;
+  const int n_tiles = CAUSAL ? min(n_tiles_all, (q_off + q0 + 63) / 64 + 1) : n_tiles_all;
 
   load_tile<HD>(sQ, qg, a.q_ss, q0, S);
-  load_tile<HD>(sK, kg, a.k_ss, 0, S);
-  load_tile<HD>(sV, vg, a.v_ss, 0, S);
+  load_tile<HD>(sK, kg, a.k_ss, 0, S_kv);
+  load_tile<HD>(sV, vg, a.v_ss, 0, S_kv);
   cp_async_commit();
 
   uint32_t qf[HD / 16][4];
@@ -108,8 +110,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
   for (int jt = 0; jt < n_tiles; ++jt) {
     const int buf = jt & 1;
     if (jt + 1 < n_tiles) {
-      load_tile<HD>(sK + (buf ^ 1) * TILE_BYTES, kg, a.k_ss, (jt + 1) * 64, S);
-      load_tile<HD>(sV + (buf ^ 1) * TILE_BYTES, vg, a.v_ss, (jt + 1) * 64, S);
+      load_tile<HD>(sK + (buf ^ 1) * TILE_BYTES, kg, a.k_ss, (jt + 1) * 64, S_kv);
+      load_tile<HD>(sV + (buf ^ 1) * TILE_BYTES, vg, a.v_ss, (jt + 1) * 64, S_kv);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
         const int kidx = kbase + nb * 8 + (e & 1);
         const int qrow = qrow0 + (e >> 1) * 8;
         float x = bf16r(bf16r(s[nb][e]) * scale);
-        if (kidx >= S || (CAUSAL && kidx > qrow)) x = -INFINITY;
+        if (kidx >= S_kv || (CAUSAL && kidx > qrow + q_off)) x = -INFINITY;
         s[nb][e] = x;
         mx[e >> 1] = fmaxf(mx[e >> 1], x);
       }

@@ -253,7 +253,7 @@ embed_splice_kernel(const long long* __restrict__ ids, const bf16* __restrict__ 
                     bf16* __restrict__ h, int S, int D, int n_vid, int vocab) {
   const long long row = blockIdx.x;
   const int b = (int)(row / S), s = (int)(row % S);
-  const int vs = vid_start[b];
+  const int vs = vid_start != nullptr ? vid_start[b] : -1;   // null: text-only rows (prefill continuation)
   const bf16* src;
   if (vs >= 0 && s > vs && s <= vs + n_vid) {
     src = vid + ((long long)b * n_vid + (s - vs - 1)) * D;

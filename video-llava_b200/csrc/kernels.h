@@ -85,6 +85,8 @@ struct AttnArgs {
   int B, H, S, head_dim;
   float scale;
   int causal;
+  int S_kv = 0;      // number of keys (0: = S); > S when the queries continue a cached sequence
+  int q_off = 0;     // absolute position of query 0 for the causal mask (S_kv - S for a continuation)
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int init_attention_kernels();

@@ -504,15 +504,19 @@ int lm_head_argmax(vcl_handle* h, const bf16* x, long long ldx, int B, float* lo
   return 0;
 }
 
+// start_pos > 0 continues a cached sequence: the S new tokens take positions start_pos .. start_pos+S-1
+// and attend to the whole cache (multi-turn reuse; no video span in a continuation).
 int llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats, const int32_t* vid_start,
                 int B, int S, int n_layers, void* hidden_out, float* logits_out, int32_t* next_tok,
-                long long tok_stride, cudaStream_t st) {
+                long long tok_stride, cudaStream_t st, int start_pos = 0) {
   const vcl_config& c = h->cfg;
   VCL_REQUIRE(h->llm_loaded, "LLM weights are not loaded");
   VCL_REQUIRE(B > 0 && B <= c.max_batch, "B=%d outside 1..%d", B, c.max_batch);
-  VCL_REQUIRE(S > 0 && S <= c.max_seq, "S=%d outside 1..%d", S, c.max_seq);
+  VCL_REQUIRE(S > 0 && start_pos >= 0 && start_pos + S <= c.max_seq, "positions %d..%d outside the cache (max_seq %d)",
+              start_pos, start_pos + S - 1, c.max_seq);
   VCL_REQUIRE(n_layers >= 0 && n_layers <= c.llm_layers, "n_layers=%d outside 0..%d", n_layers, c.llm_layers);
-  VCL_REQUIRE(ids != nullptr && vid_start != nullptr, "ids / vid_start are required");
+  VCL_REQUIRE(ids != nullptr && (vid_start != nullptr || start_pos > 0), "ids / vid_start are required");
+  VCL_REQUIRE(start_pos == 0 || video_feats == nullptr, "a continuation cannot carry a video span");
   VCL_REQUIRE((logits_out == nullptr && next_tok == nullptr) || n_layers == c.llm_layers,
               "logits / next token need the full stack (n_layers == %d)", c.llm_layers);
   const int D = c.llm_hidden, F = c.llm_inter, H = c.llm_heads, NV = h->NV;
@@ -537,13 +541,14 @@ int llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats, cons
     VCL_TRY(launch_rmsnorm(h->l_h, D, h->l_x, D, w.ln1, M, D, c.rms_eps, st));
     VCL_TRY(gemm(h->l_x, D, w.wqkv, D, h->l_qkv, 3 * D, nullptr, nullptr, 0, M, 3 * D, D, ACT_NONE, st));
     VCL_TRY(launch_rope_kv_prefill(h->l_qkv, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin, B,
-                                   S, H, 128, c.max_seq, 0, st));
+                                   S, H, 128, c.max_seq, start_pos, st));
     AttnArgs a;
     a.q = h->l_qkv; a.q_sb = (long long)S * 3 * D; a.q_sh = 128; a.q_ss = 3 * D;
     a.k = kc_layer(h, l); a.k_sb = (long long)H * c.max_seq * 128; a.k_sh = (long long)c.max_seq * 128; a.k_ss = 128;
     a.v = vc_layer(h, l); a.v_sb = a.k_sb; a.v_sh = a.k_sh; a.v_ss = 128;
     a.o = h->l_attn; a.o_sb = (long long)S * D; a.o_sh = 128; a.o_ss = D;
     a.B = B; a.H = H; a.S = S; a.head_dim = 128; a.scale = scale; a.causal = 1;
+    a.S_kv = start_pos + S; a.q_off = start_pos;
     VCL_TRY(launch_attention(a, st));
     VCL_TRY(gemm(h->l_attn, D, w.wo, D, h->l_h, D, nullptr, h->l_h, D, M, D, D, ACT_NONE, st));
     VCL_TRY(launch_rmsnorm(h->l_h, D, h->l_x, D, w.ln2, M, D, c.rms_eps, st));
@@ -739,6 +744,14 @@ int vcl_llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats,
   VCL_REQUIRE(h != nullptr, "vcl_llm_prefill: null handle");
   return llm_prefill(h, ids, video_feats, vid_start, B, S, n_layers, hidden_out, logits_out, next_tok, 1,
                      as_stream(stream));
+}
+
+int vcl_llm_prefill_append(vcl_handle* h, const int64_t* ids, int B, int S, int start_pos, void* hidden_out,
+                           float* logits_out, int32_t* next_tok, void* stream) {
+  VCL_REQUIRE(h != nullptr && ids != nullptr, "vcl_llm_prefill_append: null argument");
+  VCL_REQUIRE(start_pos > 0, "vcl_llm_prefill_append: start_pos must be > 0 (use vcl_llm_prefill for a new sequence)");
+  return llm_prefill(h, ids, nullptr, nullptr, B, S, h->cfg.llm_layers, hidden_out, logits_out, next_tok, 1,
+                     as_stream(stream), start_pos);
 }
 
 int vcl_llm_decode_step(vcl_handle* h, const int32_t* tok_in, int B, int pos, float* logits_out,

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "vcl_clip_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "vcl_llm_prefill": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
+    "vcl_llm_prefill_append": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vcl_llm_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vcl_llm_generate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_void_p]),
@@ -280,6 +281,18 @@ class Engine:
             assert vf.shape == (B, self.NV, self.cfg.clip_hidden), vf.shape
         check(lib().vcl_llm_prefill(self._h, ptr(ids.contiguous()), ptr(vf), ptr(vid_start.contiguous()), B, S,
                                     nl, ptr(hidden), ptr(logits), ptr(tok), cur_stream()))
+        return hidden, logits, tok
+
+    def prefill_append(self, ids, start_pos, want_hidden=False, want_logits=False, want_token=True):
+        """Continue the cached sequences with `ids` [B, S] (text only) at positions start_pos.. ;
+        returns (hidden [B,S,D] | None, logits [B,vocab] | None, next token [B] | None)."""
+        B, S = ids.shape
+        dev = ids.device
+        hidden = torch.empty(B, S, self.cfg.llm_hidden, dtype=torch.bfloat16, device=dev) if want_hidden else None
+        logits = torch.empty(B, self.cfg.vocab, dtype=torch.float32, device=dev) if want_logits else None
+        tok = torch.empty(B, dtype=torch.int32, device=dev) if want_token else None
+        check(lib().vcl_llm_prefill_append(self._h, ptr(ids.contiguous()), B, S, int(start_pos), ptr(hidden),
+                                           ptr(logits), ptr(tok), cur_stream()))
         return hidden, logits, tok
 
     def decode_step(self, tok_in, pos, want_logits=False):
