@@ -417,10 +417,35 @@ class VideoChatGPTLlamaForCausalLM:
         if not stepwise:
             new = eng.generate(ids, feats, vs, n).to(torch.int64)
             self._pos = S + n - 1
-            return torch.cat([ids, new], dim=1)
-        out = ids
+            self._last_out = torch.cat([ids, new], dim=1)
+            return self._last_out
         _, logits, _ = eng.prefill(ids, feats, vs, want_logits=True, want_token=False)
         self._pos = S
+        self._last_out = self._stepwise(eng, ids, logits, n, do_sample, temperature, stopping_criteria, eos_token_id)
+        return self._last_out
+
+    def generate_continue(self, new_input_ids, do_sample=False, temperature=1.0, max_new_tokens=32,
+                          stopping_criteria=None, eos_token_id=None):
+        """Next turn about the SAME video(s): `new_input_ids` [B, S_new] follow everything generated
+        so far. Only the tokens the KV cache does not hold yet (the last generated token and the new
+        text) are prefilled (vcl_llm_prefill_append); the reference re-runs the tower and the whole
+        prompt every turn (chat.py:137-154). Returns the full sequence [B, S_total + n] like generate."""
+        if getattr(self, "_last_out", None) is None:
+            raise ValueError("generate_continue: no previous generate() to continue")
+        eng = self._ensure_engine(need_llm=True)
+        prev = self._last_out
+        tail = torch.cat([prev[:, self._pos:], new_input_ids.cuda().to(torch.int64)], dim=1)
+        start = self._pos
+        ctx = torch.cat([prev, new_input_ids.cuda().to(torch.int64)], dim=1)
+        n = min(max_new_tokens, self._max_seq - ctx.shape[1])
+        if n <= 0:
+            raise ValueError(f"context length {ctx.shape[1]} leaves no room in max_seq {self._max_seq}")
+        _, logits, _ = eng.prefill_append(tail, start, want_logits=True, want_token=False)
+        self._pos = ctx.shape[1]
+        self._last_out = self._stepwise(eng, ctx, logits, n, do_sample, temperature, stopping_criteria, eos_token_id)
+        return self._last_out
+
+    def _stepwise(self, eng, out, logits, n, do_sample, temperature, stopping_criteria, eos_token_id):
         for _ in range(n):
             if do_sample and temperature > 0:
                 probs = torch.softmax(logits / temperature, dim=-1)
