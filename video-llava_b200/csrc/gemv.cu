@@ -1,9 +1,12 @@
-// Decode-time projections: out[b, n] = x[b, :] . W[n, :] for B <= 4 new tokens.
+// Decode-time projections: out[b, n] = x[b, :] . W[n, :] for B <= 4 new tokens, CUDA-core version
+// over the ROW-MAJOR weights. The default path for 1..4 clips is gemv_tc.cu (bulk-copy ring over a
+// slot-ordered weight copy + mma.sync, ~7 % faster); the launch_gemv_* entry points below route
+// there when that copy exists and the shape fits, and fall back to this kernel otherwise
+// (VCL_GEMV_LEGACY=1, VCL_NO_TILED_WEIGHTS=1, matrices with fewer than 16 rows per SM).
 //
 // With one token per clip every weight byte is used once per step (13.2 GB per step for the 7B
-// model), so these kernels are pure HBM streaming. Tensor cores are
-// deliberately not used (M = B <= 4 would waste >96 % of an MMA tile and the bound is HBM either
-// way); B > 4 goes through the tcgen05 GEMM with a narrow N tile instead.
+// model), so these kernels are pure HBM streaming; 5 <= B <= 16 uses
+// gemv_mma.cu, larger batches the tcgen05 GEMM with a narrow N tile.
 //
 // Work decomposition (one CTA = 16 warps = 512 threads):
 //   * the N weight rows are cut into equal contiguous blocks, one per CTA (grid ~ #SMs, so every

@@ -1,4 +1,5 @@
-// Decode-time projections for SMALL BATCHES (2 <= B <= 16): out[b, n] = x[b, :] . W[n, :].
+// Decode-time projections for SMALL BATCHES (5 <= B <= 16; 2..4 when gemv_tc.cu does not apply):
+// out[b, n] = x[b, :] . W[n, :].
 //
 // Still pure weight streaming (every weight byte is used once per step), but B dot products per
 // weight row on the CUDA cores cost ~50 instructions per 16-byte chunk and per batch row of

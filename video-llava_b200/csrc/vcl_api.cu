@@ -87,7 +87,7 @@ struct vcl_handle {
   float *att_stats = nullptr, *att_part = nullptr;
   unsigned int* mega_barrier = nullptr;
   unsigned long long *h_tag = nullptr, *act_tag = nullptr;   // tagged hand-off copies of d_h / d_act (gemv_tc chains)
-  bool use_mega = true;
+  bool use_mega = false;     // VCL_MEGAKERNEL=1: one persistent kernel per decode step (slower, kept for study)
   bool force_legacy_attention = false;
 
   size_t cache_layer_elems() const {
