@@ -86,7 +86,10 @@ void vcl_destroy(vcl_handle* h);
 /* Replace CLIPVisionModel.from_pretrained / VideoChatGPTLlamaForCausalLM.from_pretrained +
  * load_state_dict (eval/model_utils.py:104,122-127,134): repack into the kernel layouts
  * (fused q|k|v, interleaved gate/up, K-padded patch-embed matrix). Unknown names are ignored
- * (e.g. vision_model.post_layernorm.*, unused by the path); a missing required name is an error. */
+ * (e.g. vision_model.post_layernorm.*, unused by the path); a missing required name is an error.
+ * vcl_load_llm_weights additionally builds a decode-only copy of the streamed matrices in the slot
+ * order of the single-clip decode kernel (+1x the LLM weight bytes; VCL_NO_TILED_WEIGHTS=1 in the
+ * environment skips it and decode falls back to the row-major kernels). */
 int vcl_load_clip_weights(vcl_handle* h, const vcl_tensor* tensors, int n);
 int vcl_load_llm_weights(vcl_handle* h, const vcl_tensor* tensors, int n);
 
