@@ -23,6 +23,11 @@ Outputs (all small; see tests/test_oracle_cpu.py and tests/test_parity_gpu.py fo
   config1.npz     BASELINE config 1: 8 frames, full 24-layer ViT-L/14 -> pooled [356,1024] (fp32 run)
   llm_tiny.npz    2-layer LLaMA (hidden 512, 4 heads), B=2, S=448: last-row logits, hidden slices,
                   8 greedy tokens per clip; plus the malformed-span error behaviour
+  bf16_tiny.npz   the same two tiny models cast to bf16 (the benchmark dtype) and run by the reference /
+                  HF on CPU: hidden states, logits and greedy ids stored as raw bf16 bit patterns
+                  (uint16), so the oracle's bf16 ROUNDING POINTS are pinned bit for bit, not just its
+                  fp32 arithmetic. `rotary_emb.inv_freq` stays fp32, as `from_pretrained(torch_dtype=
+                  bf16)` leaves it (a blanket `.to(bf16)` would round the rotary frequencies too).
 """
 import importlib.util
 import os
@@ -190,6 +195,29 @@ def main():
         greedy_tokens=toks.numpy(), greedy_logits_top=torch.topk(logs, 4, dim=-1).values.numpy(),
         n_hidden_states=np.int64(len(hsl)), bad_span_error=np.array(err))
     print("llm_tiny: tokens", toks.tolist(), "error text:", err)
+
+    # ---------------- bf16_tiny: the same models in the benchmark dtype ----------------
+    bits = lambda t: t.contiguous().view(torch.int16).numpy().view(np.uint16)
+    inv = [m_.inv_freq.clone() for m_ in llm.modules() if hasattr(m_, "inv_freq")]
+    llm_b = llm.to(torch.bfloat16)
+    for m_, f in zip([m_ for m_ in llm_b.modules() if hasattr(m_, "inv_freq")], inv):
+        m_.inv_freq = f                                   # keep the rotary frequencies fp32
+        if hasattr(m_, "original_inv_freq"):
+            m_.original_inv_freq = f
+    vfb = vfe.bfloat16()
+    outb = llm_b(input_ids=ids, video_spatio_temporal_features=vfb, output_hidden_states=True, use_cache=True)
+    toksb, logsb = ref_greedy(llm_b, ids, vfb, 8)
+    clip_b = clip.to(torch.bfloat16)
+    hsb = clip_b(px.bfloat16(), output_hidden_states=True).hidden_states
+    np.savez_compressed(
+        os.path.join(HERE, "bf16_tiny.npz"),
+        llm_logits_last=bits(outb.logits[:, -1]),
+        llm_h0_rows=bits(outb.hidden_states[0][:, 60:72]), llm_h1_slice=bits(outb.hidden_states[1][:, ::37, :64]),
+        llm_h2_last=bits(outb.hidden_states[2][:, -1]),
+        llm_greedy_tokens=toksb.numpy(), llm_greedy_top4=bits(torch.topk(logsb.bfloat16(), 4, dim=-1).values),
+        **{f"clip_h{i}_slice": bits(hsb[i][:, :6, :96]) for i in range(3)},
+        clip_h2_rows=bits(hsb[2][:, ::64, ::8]))
+    print("bf16_tiny: tokens", toksb.tolist())
 
 
 if __name__ == "__main__":

@@ -118,3 +118,31 @@ def test_splice_errors_match_reference():
     shifted[0, 64 + 358] = cfg.vid_end_token
     with pytest.raises(ValueError):
         O.splice_embeddings(sd, cfg, shifted, torch.zeros(1, 356, 1024))
+
+
+@torch.no_grad()
+def test_bf16_rounding_points_bit_exact_vs_reference():
+    """bf16_tiny.npz holds raw bf16 bit patterns produced by the REFERENCE forward / HF CLIP in bf16 on
+    this CPU (rotary inv_freq kept fp32). The oracle run in bf16 must reproduce them bit for bit: this
+    pins every bf16 rounding point of the restatement, which is what the GPU kernels are built to match."""
+    g = _load("bf16_tiny.npz")
+    bits = lambda t: t.contiguous().view(torch.int16).numpy().view(np.uint16)
+    bf = lambda sd: {k: v.bfloat16() for k, v in sd.items()}
+    cfg = O.LlmCfg(hidden=512, inter=1024, heads=4, layers=2)
+    sd = bf(O.random_llm_state(cfg, seed=21))
+    ids = O.make_prompt_ids(cfg, 356, seed=1, batch=2)
+    vf = (torch.randn(2, 356, 1024, generator=torch.Generator().manual_seed(9)) * 0.5).half().float().bfloat16()
+    logits, hs, _ = O.llm_forward(sd, cfg, ids, vf)
+    assert np.array_equal(bits(hs[0][:, 60:72]), g["llm_h0_rows"])
+    assert np.array_equal(bits(hs[1][:, ::37, :64]), g["llm_h1_slice"])
+    assert np.array_equal(bits(hs[2][:, -1]), g["llm_h2_last"])
+    assert np.array_equal(bits(logits[:, -1]), g["llm_logits_last"])
+    toks, logs = O.greedy_generate(sd, cfg, ids, vf, 8)
+    assert np.array_equal(toks.numpy(), g["llm_greedy_tokens"])
+    assert np.array_equal(bits(torch.topk(logs.bfloat16(), 4, dim=-1).values), g["llm_greedy_top4"])
+    ccfg = O.ClipCfg(hidden=1024, inter=1024, heads=16, layers=3)
+    csd = bf(O.random_clip_state(ccfg, seed=11))
+    hsc = O.clip_hidden_states(csd, ccfg, O.preprocess_frames(O.make_frames(7, 3)).bfloat16(), n_layers=2)
+    for i in range(3):
+        assert np.array_equal(bits(hsc[i][:, :6, :96]), g[f"clip_h{i}_slice"]), i
+    assert np.array_equal(bits(hsc[2][:, ::64, ::8]), g["clip_h2_rows"])
