@@ -97,9 +97,11 @@ int vcl_load_llm_weights(vcl_handle* h, const vcl_tensor* tensors, int n);
  * (video_chatgpt/inference.py:93-94, scripts/save_spatio_temporal_clip_features.py:116-120).
  * Runs `n_layers` encoder layers (<= clip_layers; pass clip_layers for hidden_states[-2]; 0 gives
  * hidden_states[0], the post-pre_layrnorm embeddings). hidden_out is [n_frames, 1+P, C] bf16 with
- * the CLS row kept, as in HF; callers slice [:, 1:]. */
-int vcl_clip_encode(vcl_handle* h, const void* pixels, int pixel_format, int n_frames, int n_layers,
-                    void* hidden_out, void* stream);
+ * the CLS row kept, as in HF; callers slice [:, 1:]. frame_h / frame_w are the height and width of
+ * the frames behind `pixels`: they must equal image_size (the image processor of the reference
+ * resizes and crops, inference.py:86; raw frames of another size are an error, never read out of bounds). */
+int vcl_clip_encode(vcl_handle* h, const void* pixels, int pixel_format, int n_frames, int frame_h, int frame_w,
+                    int n_layers, void* hidden_out, void* stream);
 
 /* get_spatio_temporal_features_torch (video_chatgpt/inference.py:13-44) and its numpy twin
  * get_spatio_temporal_features (scripts/save_spatio_temporal_clip_features.py:46-57).
@@ -110,12 +112,13 @@ int vcl_st_pool(const void* feats, int in_dtype, int64_t frame_stride, int64_t p
 
 /* vcl_clip_encode(clip_layers) + CLS drop + vcl_st_pool in one call: the per-video body of
  * scripts/save_spatio_temporal_clip_features.py:105-123 and inference.py:93-95. */
-int vcl_clip_features(vcl_handle* h, const void* pixels, int pixel_format, int n_frames, void* out,
-                      int out_dtype, void* stream);
+int vcl_clip_features(vcl_handle* h, const void* pixels, int pixel_format, int n_frames, int frame_h, int frame_w,
+                      void* out, int out_dtype, void* stream);
 
 /* VideoChatGPTLlamaForCausalLM.forward on a full prompt (video_chatgpt/model/video_chatgpt.py:82-175,
  * 193-251): token embedding, mm_projector on video_feats [B, n_temporal+P, 1024], splice after
- * <vid_start> (vid_start[b] = index of that token in row b, or -1 for a text-only row), n_layers
+ * <vid_start> (vid_start[b] = index of the row after which the video rows go: the <vid_start> token, or
+ * -1 when the patch tokens start the row without one; VCL_NO_VIDEO marks a text-only row), n_layers
  * decoder layers filling the KV cache at positions [0, S).
  *   hidden_out  optional [B,S,D] bf16: output of decoder layer n_layers (n_layers = 0: the spliced
  *               input embeddings), i.e. HF hidden_states[n_layers]
@@ -125,6 +128,15 @@ int vcl_clip_features(vcl_handle* h, const void* pixels, int pixel_format, int n
 int vcl_llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats,
                     const int32_t* vid_start, int B, int S, int n_layers, void* hidden_out,
                     float* logits_out, int32_t* next_tok, void* stream);
+#define VCL_NO_VIDEO (-2147483647 - 1)
+
+/* forward(..., output_hidden_states=True) (video_chatgpt/model/video_chatgpt.py:205-218): the same
+ * full-depth prefill, keeping every hidden state: states_out is [llm_layers + 1][B][S][D] bf16, entry i
+ * = the raw output of decoder layer i (entry 0: the spliced input embeddings). HF returns the LAST
+ * entry after the final RMSNorm; the caller applies it (vcl_op_rmsnorm with model.norm.weight). */
+int vcl_llm_prefill_states(vcl_handle* h, const int64_t* ids, const void* video_feats,
+                           const int32_t* vid_start, int B, int S, void* states_out, float* logits_out,
+                           void* stream);
 
 /* Continue a cached sequence: S more token ids per clip (text only, no video span) take positions
  * [start_pos, start_pos + S) and attend to everything already in the KV cache. This is the building

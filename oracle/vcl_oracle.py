@@ -86,7 +86,8 @@ def preprocess_frames(frames_u8: np.ndarray | torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------
 # CLIP ViT
 # ---------------------------------------------------------------------------------------------
-def clip_hidden_states(sd: dict, cfg: ClipCfg, pixel_values: torch.Tensor, n_layers: int | None = None):
+def clip_hidden_states(sd: dict, cfg: ClipCfg, pixel_values: torch.Tensor, n_layers: int | None = None,
+                       attn: str = "eager"):
     """Returns [hidden_states[0], ..., hidden_states[n_layers]] exactly as HF's
     CLIPVisionModel(..., output_hidden_states=True): [0] is the post-pre_layrnorm embedding,
     [i] the output of encoder layer i. The path consumes index cfg.layers-1 (hidden_states[-2])."""
@@ -115,9 +116,12 @@ def clip_hidden_states(sd: dict, cfg: ClipCfg, pixel_values: torch.Tensor, n_lay
         q = q.view(n, s, cfg.heads, hd).transpose(1, 2)
         k = k.view(n, s, cfg.heads, hd).transpose(1, 2)
         v = v.view(n, s, cfg.heads, hd).transpose(1, 2)
-        w = torch.matmul(q, k.transpose(-1, -2)) * scale
-        w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
-        a = torch.matmul(w, v).transpose(1, 2).reshape(n, s, cfg.hidden)
+        if attn == "sdpa":      # library-baseline timing only (bench.py); parity is defined on the eager form
+            a = F.scaled_dot_product_attention(q, k, v, scale=scale).transpose(1, 2).reshape(n, s, cfg.hidden)
+        else:
+            w = torch.matmul(q, k.transpose(-1, -2)) * scale
+            w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
+            a = torch.matmul(w, v).transpose(1, 2).reshape(n, s, cfg.hidden)
         a = F.linear(a, sd[lp + "self_attn.out_proj.weight"], sd[lp + "self_attn.out_proj.bias"])
         h = r + a
         r = h
@@ -216,7 +220,8 @@ def _rotate_half(x):
 
 
 def llm_forward(sd: dict, cfg: LlmCfg, ids: torch.Tensor, feats: torch.Tensor | None = None,
-                past: list | None = None, n_layers: int | None = None, all_logits: bool = False):
+                past: list | None = None, n_layers: int | None = None, all_logits: bool = False,
+                attn: str = "eager"):
     """One forward of VideoChatGPTLlamaForCausalLM. `past` is a list of (k, v) per layer
     ([B,H,S,hd]); with a past the video features are ignored exactly as the reference does for
     single-token inputs (video_chatgpt.py:103). Returns (logits, hidden_states, past) where
@@ -255,11 +260,17 @@ def llm_forward(sd: dict, cfg: LlmCfg, ids: torch.Tensor, feats: torch.Tensor | 
             k = torch.cat([past[l][0], k], dim=2)
             v = torch.cat([past[l][1], v], dim=2)
         new_past.append((k, v))
-        w = torch.matmul(q, k.transpose(2, 3)) * scale
-        if mask is not None:
-            w = w + mask
-        w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
-        a = torch.matmul(w, v).transpose(1, 2).reshape(b, s, cfg.hidden)
+        if attn == "sdpa":
+            # what transformers 5.x picks by default ($TF/integrations/sdpa_attention.py); used only to
+            # screen prompts for eager-vs-sdpa self-agreement, never as the parity target
+            a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, scale=scale)
+            a = a.transpose(1, 2).reshape(b, s, cfg.hidden)
+        else:
+            w = torch.matmul(q, k.transpose(2, 3)) * scale
+            if mask is not None:
+                w = w + mask
+            w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
+            a = torch.matmul(w, v).transpose(1, 2).reshape(b, s, cfg.hidden)
         h = r + F.linear(a, sd[lp + "self_attn.o_proj.weight"])
         r = h
         y = _rmsnorm(h, sd[lp + "post_attention_layernorm.weight"], cfg.rms_eps)
@@ -275,12 +286,12 @@ def llm_forward(sd: dict, cfg: LlmCfg, ids: torch.Tensor, feats: torch.Tensor | 
 
 
 def greedy_generate(sd: dict, cfg: LlmCfg, ids: torch.Tensor, feats: torch.Tensor, n_new: int,
-                    forced: torch.Tensor | None = None):
+                    forced: torch.Tensor | None = None, attn: str = "eager"):
     """Greedy decoding with a KV cache, EOS ignored. If `forced` ([B, n_new]) is given the loop is
     teacher-forced with those tokens (the arg-max of every step is still reported).
     Returns (tokens [B,n_new] int64, last-position logits per step [n_new,B,V] fp32)."""
     toks, logs = [], []
-    logits, _, past = llm_forward(sd, cfg, ids, feats)
+    logits, _, past = llm_forward(sd, cfg, ids, feats, attn=attn)
     for i in range(n_new):
         lg = logits[:, -1].float()
         logs.append(lg)
@@ -289,7 +300,7 @@ def greedy_generate(sd: dict, cfg: LlmCfg, ids: torch.Tensor, feats: torch.Tenso
         if i + 1 == n_new:
             break
         feed = nxt if forced is None else forced[:, i].to(nxt.device)
-        logits, _, past = llm_forward(sd, cfg, feed[:, None], feats, past)
+        logits, _, past = llm_forward(sd, cfg, feed[:, None], feats, past, attn=attn)
     return torch.stack(toks, 1), torch.stack(logs, 0)
 
 
@@ -370,3 +381,32 @@ def random_llm_state(cfg: LlmCfg, seed: int = 0, dtype=torch.float32) -> dict:
         sd[lp + "input_layernorm.weight"] = 1 + r(d, std=0.05)
         sd[lp + "post_attention_layernorm.weight"] = 1 + r(d, std=0.05)
     return {k: v.to(dtype) for k, v in sd.items()}
+
+
+def device_llm_state(cfg: LlmCfg, device, seed: int = 0, dtype=torch.bfloat16) -> dict:
+    """Full-size random-init LLM weights generated ON the device in `dtype` (a 7B fp32 state built on
+    the host takes minutes and 27 GB); same distributions as random_llm_state, different bytes."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    big = lambda r, c, std: torch.empty(r, c, device=device, dtype=dtype).normal_(0.0, std, generator=g)
+    vec = lambda n, std: torch.empty(n, device=device, dtype=torch.float32).normal_(0.0, std, generator=g)
+    d, f = cfg.hidden, cfg.inter
+    sd = {"model.embed_tokens.weight": big(cfg.vocab, d, 1.0), "model.norm.weight": (1 + vec(d, 0.05)).to(dtype),
+          "lm_head.weight": big(cfg.vocab, d, d ** -0.5)}
+    if cfg.proj_type == "linear":
+        sd["model.mm_projector.weight"] = big(d, cfg.mm_hidden, cfg.mm_hidden ** -0.5)
+        sd["model.mm_projector.bias"] = vec(d, 0.02).to(dtype)
+    else:
+        sd["model.mm_projector.0.weight"] = big(d, cfg.mm_hidden, cfg.mm_hidden ** -0.5)
+        sd["model.mm_projector.0.bias"] = vec(d, 0.02).to(dtype)
+        sd["model.mm_projector.2.weight"] = big(d, d, d ** -0.5)
+        sd["model.mm_projector.2.bias"] = vec(d, 0.02).to(dtype)
+    for l in range(cfg.layers):
+        lp = f"model.layers.{l}."
+        for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[lp + f"self_attn.{nm}.weight"] = big(d, d, d ** -0.5)
+        sd[lp + "mlp.gate_proj.weight"] = big(f, d, d ** -0.5)
+        sd[lp + "mlp.up_proj.weight"] = big(f, d, d ** -0.5)
+        sd[lp + "mlp.down_proj.weight"] = big(d, f, f ** -0.5)
+        sd[lp + "input_layernorm.weight"] = (1 + vec(d, 0.05)).to(dtype)
+        sd[lp + "post_attention_layernorm.weight"] = (1 + vec(d, 0.05)).to(dtype)
+    return sd

@@ -125,3 +125,167 @@ def test_generate_continue_second_turn():
     m2 = _model(lcfg, 3, max_batch=1)
     with pytest.raises(ValueError, match="no previous generate"):
         m2.generate_continue(q2)
+
+
+@torch.no_grad()
+def test_generate_stops_at_eos_per_row_like_hf():
+    """generate() honours EOS by default. Two clips whose greedy continuations hit the
+    chosen EOS id at different steps: each row is padded after ITS EOS, the call returns when both are
+    done, greedy chunks on the device and the stepwise (sampling-style) path agree."""
+    lcfg = O.LlmCfg(hidden=512, inter=1024, heads=4, layers=2)
+    m = _model(lcfg, 3, max_batch=2)
+    m.load_state_dict(O.random_llm_state(lcfg, seed=21))
+    feats = (torch.randn(2, 356, 1024, generator=torch.Generator().manual_seed(4)) * 0.5).half().cuda()
+    ids = O.make_prompt_ids(lcfg, 356, seed=3, batch=2).cuda()
+    free = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=40, eos_token_id=None)
+    assert free.shape == (2, 448 + 40)
+    new = free[:, 448:]
+    eos = int(new[0, 5])                                   # row 0 finishes at step 5 (or earlier if repeated)
+    first = [int((new[b] == eos).nonzero()[0]) if (new[b] == eos).any() else None for b in range(2)]
+    out = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=40, eos_token_id=eos,
+                     pad_token_id=0)
+    got = out[:, 448:]
+    if first[1] is None:                                   # row 1 never emits it: runs to the limit
+        assert got.shape[1] == 40
+    else:
+        assert got.shape[1] == max(first) + 1
+    for b in range(2):
+        k = first[b] if first[b] is not None else got.shape[1] - 1
+        assert torch.equal(got[b, : k + 1], new[b, : k + 1])           # identical up to and including the EOS
+        assert (got[b, k + 1:] == 0).all()                              # padded afterwards
+    # the per-token path (what sampling / stopping criteria use) gives the same sequences
+    class Never:
+        def __call__(self, *a, **k): return False
+    out2 = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=40, eos_token_id=eos,
+                      pad_token_id=0, stopping_criteria=[Never()])
+    assert torch.equal(out2, out)
+    # default = config.eos_token_id (2 for LLaMA): a model that never emits 2 decodes max_new_tokens
+    assert m._eos_pad("config", None)[0] == 2
+
+
+@torch.no_grad()
+def test_forward_hidden_states_like_hf():
+    """forward(output_hidden_states=True) (reference video_chatgpt.py:205-218 over HF LlamaModel): L+1
+    tensors from one pass, the LAST one after the final RMSNorm, against the oracle."""
+    lcfg = O.LlmCfg(hidden=512, inter=1024, heads=4, layers=2)
+    m = _model(lcfg, 3, max_batch=2)
+    lsd = O.random_llm_state(lcfg, seed=21)
+    m.load_state_dict(lsd)
+    feats = (torch.randn(2, 356, 1024, generator=torch.Generator().manual_seed(9)) * 0.5).half().cuda()
+    ids = O.make_prompt_ids(lcfg, 356, seed=1, batch=2).cuda()
+    out = m(input_ids=ids, video_spatio_temporal_features=feats, output_hidden_states=True)
+    assert len(out.hidden_states) == 3 and out.logits.shape == (2, 1, lcfg.vocab)
+    bf = {k: v.cuda().bfloat16() for k, v in lsd.items()}
+    f32 = {k: v.cuda().float() for k, v in lsd.items()}
+    _, ref_hs, _ = O.llm_forward(bf, lcfg, ids, feats.bfloat16())
+    _, gold_hs, _ = O.llm_forward(f32, lcfg, ids, feats.float())
+    from _util import bar
+    for i in range(3):
+        assert out.hidden_states[i].shape == (2, 448, 512)
+        bar(out.hidden_states[i], ref_hs[i], gold_hs[i], f"forward().hidden_states[{i}]" + (" (post-norm)" if i == 2 else ""))
+
+
+@torch.no_grad()
+def test_initialize_model_and_video_chatgpt_infer_end_to_end(tmp_path):
+    """The drop-in entry points themselves (reference eval/model_utils.py:82-150, inference.py:47-125) on a
+    synthetic LOCAL checkpoint: tokenizer + config + safetensors + CLIP directory -> initialize_model ->
+    video_chatgpt_infer (PIL frames, image processor, tower, pool, generate with stop string and EOS,
+    decode), against the same steps done with the oracle."""
+    from PIL import Image
+    from _checkpoint import make_tiny_checkpoint
+    from video_chatgpt.eval.model_utils import initialize_model
+    from video_chatgpt.inference import video_chatgpt_infer
+    from video_chatgpt.video_conversation import conv_templates
+    ck = make_tiny_checkpoint(tmp_path)
+    model, tower, tok, ip, vlen = initialize_model(ck["model_dir"], max_batch=1, max_seq=1024)
+    assert vlen == 356 and len(tok) == 1003
+    vc = model.get_model().vision_config
+    assert (vc.vid_patch_token, vc.vid_start_token, vc.vid_end_token, vc.use_vid_start_end) == (1000, 1001, 1002, True)
+    assert model.state_dict()["model.embed_tokens.weight"].shape[0] == 1003 and model.config.vocab_size == 1003
+    frames = [Image.fromarray(f) for f in O.make_frames(21, 6)]
+    question = "w10 w11 w12 w13"
+    text = video_chatgpt_infer(frames, question, "pg-video-llava", model, tower, tok, ip, vlen, do_sample=False,
+                               max_new_tokens=10)
+    assert isinstance(text, str)
+
+    # the same steps with the oracle on the same (resized) weights
+    conv = conv_templates["pg-video-llava"].copy()
+    conv.append_message(conv.roles[0], question + "\n" + "<vid_start>" + "<vid_patch>" * vlen + "<vid_end>")
+    conv.append_message(conv.roles[1], None)
+    ids = torch.as_tensor(tok([conv.get_prompt()]).input_ids).cuda()
+    assert (ids == 1000).sum() == 356 and (ids == 1001).sum() == 1 and ids[0, 0] == 1
+    px = ip.preprocess(frames, return_tensors="pt")["pixel_values"].cuda().bfloat16()
+    csd = {k: v.cuda().bfloat16() for k, v in ck["clip_sd"].items()}
+    hid = O.clip_hidden_states(csd, ck["clip_cfg"], px, 2)[-1]
+    feats = O.st_pool_torch(hid[:, 1:])
+    lsd = {k: v.cuda().bfloat16() for k, v in model.state_dict().items()}
+    lcfg = O.LlmCfg(hidden=512, inter=1024, heads=4, layers=2, vocab=1003, vid_patch_token=1000, vid_start_token=1001,
+                    vid_end_token=1002)
+    o_toks, o_logits = O.greedy_generate(lsd, lcfg, ids, feats[None].bfloat16(), 10)
+    row = o_toks[0].tolist()
+    if 2 in row:
+        row = row[: row.index(2) + 1]
+    want = tok.batch_decode([row], skip_special_tokens=True)[0].strip()
+    top = torch.topk(o_logits[:, 0], 2, dim=-1).values
+    margins = (top[:, 0] - top[:, 1]) / (top[:, 0].abs().clamp_min(2 ** -6) * 2 ** -7)
+    print(f"[dropin] video_chatgpt_infer -> {text!r}; oracle -> {want!r}; min oracle margin {margins.min().item():.1f} ulps")
+    assert text.split()[:1] == want.split()[:1]
+    if margins.min() >= 3:
+        assert text == want
+
+
+def test_offline_extractor_main_format_resume_and_flush(tmp_path, monkeypatch):
+    """scripts/save_spatio_temporal_clip_features.py:main (reference :95-139) with a `decord` stub: one
+    pickle of a [356,1024] float16 ndarray per video, videos that already have a pickle are skipped,
+    pending features are written every FLUSH_EVERY processed videos and at the end; the features equal
+    the reference's numpy pooling of the tower's hidden state, and the training-side reader loads them."""
+    import importlib.util
+    import pickle
+    import sys
+    import types
+    from _checkpoint import make_tiny_checkpoint
+    ck = make_tiny_checkpoint(tmp_path)
+    vids, outd = tmp_path / "videos", tmp_path / "feats"
+    vids.mkdir()
+    clips = {f"clip{i}": O.make_frames(40 + i, 4 + i) for i in range(4)}         # 4..7 frames each
+    for name, fr in clips.items():
+        np.save(vids / f"{name}.npy", fr)
+    (vids / "broken.npy").write_bytes(b"not a video")
+    seen_at_open = {}
+
+    class VideoReader:                       # decord.VideoReader over .npy "videos"
+        def __init__(self, path, ctx=None):
+            seen_at_open[os.path.basename(path)] = sorted(os.listdir(outd))
+            self.arr = np.load(path)
+        def __len__(self): return len(self.arr)
+        def get_batch(self, idx): return types.SimpleNamespace(asnumpy=lambda: self.arr[list(idx)])
+    monkeypatch.setitem(sys.modules, "decord", types.SimpleNamespace(VideoReader=VideoReader, cpu=lambda i: None))
+    spec = importlib.util.spec_from_file_location(
+        "vcl_save_feats_main", os.path.join(os.path.dirname(G), "..", "video-llava_b200", "scripts",
+                                            "save_spatio_temporal_clip_features.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    outd.mkdir()
+    with open(outd / "clip1.pkl", "wb") as f:                                   # "already processed": must be skipped
+        pickle.dump("sentinel", f)
+    monkeypatch.setattr(mod, "FLUSH_EVERY", 2)
+    monkeypatch.setattr(sys, "argv", ["x", "--llava", "1.1", "--video_dir_path", str(vids), "--clip_feat_path", str(outd),
+                                      "--clip_dir", ck["clip_dir"]])
+    mod.main()
+    assert sorted(os.listdir(outd)) == ["clip0.pkl", "clip1.pkl", "clip2.pkl", "clip3.pkl"]     # broken.npy: reported, no file
+    assert pickle.load(open(outd / "clip1.pkl", "rb")) == "sentinel" and "clip1.npy" not in seen_at_open
+    # flush after every 2 processed videos: when the third processed video (clip3) is opened, the first two are on disk
+    assert {"clip0.pkl", "clip2.pkl"} <= set(seen_at_open["clip3.npy"])
+    from video_chatgpt.train import collate_video_features, load_video_features
+    csd = {k: v.cuda().bfloat16() for k, v in ck["clip_sd"].items()}
+    batch = []
+    for name in ("clip0", "clip2", "clip3"):
+        f = load_video_features(str(outd), f"{name}.pkl")
+        assert isinstance(f, np.ndarray) and f.dtype == np.float16 and f.shape == (356, 1024)
+        T = len(clips[name])
+        assert (f[T:100] == 0).all() and np.abs(f[:T]).sum() > 0
+        hid = O.clip_hidden_states(csd, ck["clip_cfg"], O.preprocess_frames(clips[name]).cuda().bfloat16(), 2)[-1]
+        ref = O.st_pool_numpy(hid[:, 1:].float().cpu().numpy().astype("float16"))
+        err = np.linalg.norm(f.astype(np.float32) - ref.astype(np.float32)) / np.linalg.norm(ref.astype(np.float32))
+        assert err < 2e-2, (name, err)
+        batch.append({"video": f})
+    assert collate_video_features(batch).shape == (3, 356, 1024)

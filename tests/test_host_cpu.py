@@ -119,9 +119,11 @@ def test_video_span_validation_errors(built):
     with pytest.raises(ValueError, match="video end token should follow"):
         m._video_spans(shifted, 356)
     text_only = torch.randint(3, 1000, (1, 32))
-    assert m._video_spans(text_only, 356) == [-1]
+    assert m._video_spans(text_only, 356) == [built.NO_VIDEO] and built.NO_VIDEO == -2 ** 31
     vc.use_vid_start_end = False
     assert m._video_spans(ids, 356) == [64, 64]                      # rows 65..420 replaced either way
+    lead = torch.cat([torch.full((1, 356), 32000), torch.randint(3, 1000, (1, 8))], 1)
+    assert m._video_spans(lead, 356) == [-1]                         # patch tokens from row 0: a real span, not "no video"
     with pytest.raises(ValueError, match="number of video patch tokens"):
         m._video_spans(ids, 300)
     # state handling: resize_token_embeddings pads with the mean row, strict load rejects unknown keys
@@ -135,6 +137,62 @@ def test_video_span_validation_errors(built):
     kw = m.prepare_inputs_for_generation(ids, past_key_values=None, video_spatio_temporal_features="f")
     assert kw["input_ids"].shape == ids.shape and kw["video_spatio_temporal_features"] == "f"
     assert m.prepare_inputs_for_generation(ids, past_key_values=7)["input_ids"].shape == (2, 1)
+
+
+def test_eos_defaults_and_finished_row_masking(built):
+    """HF generate stops at config.eos_token_id implicitly: the mirror's defaults and the
+    padding of finished rows, on CPU tensors."""
+    from video_chatgpt.model import VideoChatGPTConfig, VideoChatGPTLlamaForCausalLM
+    cfg = VideoChatGPTConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=4,
+                             vocab_size=32003, use_mm_proj=True, mm_hidden_size=1024)
+    m = VideoChatGPTLlamaForCausalLM(cfg, clip_config={})
+    assert m._eos_pad("config", None) == (2, 2)                      # LLaMA default, pad falls back to eos
+    assert m._eos_pad(None, None) == (None, None)                    # explicit None: fixed-length decoding
+    cfg.eos_token_id, cfg.pad_token_id = 7, 0
+    assert m._eos_pad("config", None) == (7, 0) and m._eos_pad(5, 9) == (5, 9)
+    new = torch.tensor([[4, 7, 3, 3], [4, 5, 6, 8]])
+    out, done = m._mask_finished(new, 7, 0)
+    assert not done and out.tolist() == [[4, 7, 0, 0], [4, 5, 6, 8]]  # row 0 finished: padded after its EOS
+    new = torch.tensor([[4, 7, 3, 3], [4, 5, 7, 8]])
+    out, done = m._mask_finished(new, 7, 0)
+    assert done and out.tolist() == [[4, 7, 0], [4, 5, 7]]            # all finished: cut at the longest row
+
+
+def test_stop_string_cannot_catch_eos_with_a_bos_prepending_tokenizer(built, tmp_path):
+    """With a LLaMA-like tokenizer "</s>" -> [bos, eos]: the stop criterion has no keyword id and the
+    decoded text drops the special token, so only the EOS id passed to generate() can stop the loop."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _checkpoint import make_tiny_checkpoint
+    from transformers import AutoTokenizer
+    from video_chatgpt.model.utils import KeywordsStoppingCriteria
+    ck = make_tiny_checkpoint(tmp_path)
+    tok = AutoTokenizer.from_pretrained(ck["model_dir"])
+    assert tok("</s>").input_ids == [1, 2] and tok.eos_token_id == 2
+    prompt = torch.tensor([[1, 7, 8]])
+    crit = KeywordsStoppingCriteria(["</s>"], tok, prompt)
+    assert crit.keyword_ids == []
+    crit(prompt)
+    assert crit(torch.tensor([[1, 7, 8, 9, 2]])) is False            # EOS generated, criterion blind to it
+
+
+def test_training_side_reader_round_trip(built, tmp_path):
+    """The on-disk format of the extractor (one pickle of a [100+P,1024] float16 ndarray per video) as
+    the reference's trainer consumes it (train/train.py:401-405, 447-452)."""
+    import pickle
+    import numpy as np
+    from video_chatgpt.train import collate_video_features, load_video_features
+    a = np.random.default_rng(0).standard_normal((356, 1024)).astype(np.float16)
+    b = np.random.default_rng(1).standard_normal((356, 1024)).astype(np.float16)
+    for name, arr in (("v1.pkl", a), ("v2.pkl", b)):
+        with open(tmp_path / name, "wb") as f:
+            pickle.dump(arr, f)
+    fa, fb = load_video_features(str(tmp_path), "v1.pkl"), load_video_features(str(tmp_path), "v2.pkl")
+    assert isinstance(fa, np.ndarray) and fa.dtype == np.float16 and fa.shape == (356, 1024)
+    batch = collate_video_features([{"video": fa}, {"video": fb}])
+    assert batch.shape == (2, 356, 1024) and batch.dtype == torch.float16
+    assert np.array_equal(batch[1].numpy(), b)
+    ragged = collate_video_features([{"video": fa}, {"video": fb[:300]}])
+    assert isinstance(ragged, list) and ragged[1].shape == (300, 1024)
 
 
 def _dp_worker(rank, world, port, n_clips, ret):

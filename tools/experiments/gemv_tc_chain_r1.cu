@@ -56,7 +56,7 @@ constexpr int TC_DEFAULT_SLOTS = 8;                 // measured optimum (7 B sha
 constexpr int TC_SMEM_BUDGET = 160 * 1024;          // one CTA per SM; the rest of the SM stays free for the
                                                     // attention kernel's CTAs, which launch early (PDL)
 
-constexpr int TC_MAX_PHASES = 1;     // (a chain of dependent phases per launch was tried in round 1: tools/experiments/)
+constexpr int TC_MAX_PHASES = 4;
 
 struct TcParams {
   TcPhase ph[TC_MAX_PHASES];        // dependent projections executed back to back by one launch
@@ -68,7 +68,7 @@ struct TcParams {
   float eps;
   const bf16* cos_t; const bf16* sin_t;
   int H, s_max, pos;
-  const int* pos_dev;               // position = pos + *pos_dev (one captured graph for every prompt length)
+  unsigned* gen_counter;            // launch generation of the tagged hand-off buffers (multi-phase launches)
   unsigned long long* trace;        // optional [grid][TC_MAX_PHASES][8] timestamps (VCL_TC_TRACE)
 };
 
@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
   // =============================== consumers ===============================
   constexpr int XU = 7;                               // 16-byte chunks per thread: K <= 14336
   const int g = lane >> 2, q = lane & 3;
+  unsigned gen = 0;
   for (int i = 0; i < p.n_phases; ++i) {
     const TcPhase& ph = p.ph[i];
     const int K = ph.K, N = ph.N, mode = ph.mode;
@@ -198,49 +199,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
     float ss = 0.f;
     if (i == 0) {
       pdl_wait();                                    // the first activation vector comes from the previous kernel
-      if (tid == 0) trace(i, 1);
+      if (tid == 0) {
+        trace(i, 1);
+        if (p.n_phases > 1) {
+          unsigned b;
+          asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(b) : "l"(p.gen_counter) : "memory");
+          red[8] = __uint_as_float(b);
+        }
+      }
       for (int b = 0; b < NB; ++b) {                  // one clip after the other (one L2 round trip each)
         bf16* xb = xs + (size_t)b * K;
         const bf16* xg = ph.x + (long long)b * ph.ldx;
-        if (ph.embed != nullptr) {
-          // fused token-embedding gather: x = embed[token]. The token is either given (first step
-          // of a decode loop) or the arg-max of the previous step's logits, whose per-CTA partials
-          // every warp reduces for itself (same result in every warp: no barrier needed)
-          int tok;
-          if (ph.amax_in != nullptr) {
-            float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int c = lane; c < ph.amax_n; c += 32) {
-              float v; int ix;
-              asm volatile("ld.global.cg.v2.b32 {%0,%1}, [%2];" : "=f"(v), "=r"(ix) : "l"(ph.amax_in + (size_t)c * NB + b) : "memory");
-              if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            tok = bi;
-            if (blockIdx.x == 0 && tid == 0 && ph.tok_out != nullptr) ph.tok_out[(long long)b * ph.tok_out_stride] = tok;
-          } else {
-            asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(tok) : "l"(ph.tok_in + (long long)b * ph.tok_stride) : "memory");
-          }
-          tok = tok < 0 ? 0 : (tok >= ph.vocab ? ph.vocab - 1 : tok);
-          xg = ph.embed + (long long)tok * K;
-        }
         uint4 xv[XU];
 #pragma unroll
         for (int u = 0; u < XU; ++u) {
           const int c = tid + u * TC_CONSUMERS;
           xv[u] = (c < nch) ? ld_cg_v4(xg + c * 8) : make_uint4(0, 0, 0, 0);
-        }
-        if (ph.embed != nullptr && ph.h_out != nullptr && blockIdx.x == 0) {
-          // the raw embedding row is the residual stream of layer 0 (read by o_proj's epilogue)
-#pragma unroll
-          for (int u = 0; u < XU; ++u) {
-            const int c = tid + u * TC_CONSUMERS;
-            if (c < nch) *reinterpret_cast<uint4*>(ph.h_out + (long long)b * K + c * 8) = xv[u];
-          }
         }
         if (ph.norm_w != nullptr) {
           ss = 0.f;
@@ -282,6 +256,84 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
           }
         }
       }
+      cbar();
+    } else {
+      // ---- phase i reads what every CTA wrote in phase i-1: tagged hand-off, no barrier, no fence ----
+      // The producers of the vector store 8-byte units {bf16 v0, bf16 v1, u32 generation} with ONE
+      // 64-bit store each (single-copy atomic), the consumers poll every unit until its generation is
+      // the expected one: a unit is either entirely old or entirely new, so no memory fence is needed
+      // (a gpu-scope fence costs ~3 us here while bulk copies are in flight) and a CTA waits exactly
+      // for the data it reads. All CTAs of the launch are resident (a CTA takes more than half an SM
+      // and the next launch cannot start before every CTA of this one has started).
+      const unsigned want = __float_as_uint(red[8]) * 8u + (unsigned)i;
+      const int n_units = K >> 1;
+      // Waiting is done by ONE warp on ONE unit per producing CTA (the last unit of its block), with
+      // a pause between polls: when every thread polls the units it needs, ~38 000 pollers queue up
+      // on the two or three L2 lines the slowest CTA has still to write and slow down that very CTA.
+      // The per-unit generation check below stays (it is what makes the hand-off correct); after
+      // this it practically never has to spin.
+      if (warp == 0) {
+        const TcPhase& prev = p.ph[i - 1];
+        const int pg = (prev.N + 15) >> 4;
+        for (int cta = lane; cta < (int)gridDim.x; cta += 32) {
+          const int ge = (int)(((long long)(cta + 1) * pg) / gridDim.x);            // end of that CTA's row groups
+          const int elem_end = (prev.mode == TC_MODE_RES) ? ge * 16 : ge * 8;
+          const unsigned long long* sentinel = ph.x_tagged + ((elem_end - 2) >> 1);
+          unsigned long long v;
+          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(sentinel) : "memory");
+          for (int spin = 0; (unsigned)(v >> 32) != want && spin < (1 << 19); ++spin) {
+            __nanosleep(64);
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(sentinel) : "memory");
+          }
+        }
+      }
+      cbar();
+      constexpr int UB = 12;                          // units per thread and batch (K <= 6144 in one batch)
+      const bool normed = ph.norm_w != nullptr;      // (normed phases have K = hidden size: one batch)
+      for (int u0 = 0; u0 < n_units; u0 += UB * TC_CONSUMERS) {
+        unsigned long long uv[UB];
+#pragma unroll
+        for (int b = 0; b < UB; ++b) {
+          const int u = u0 + tid + b * TC_CONSUMERS;
+          uv[b] = 0;
+          if (u < n_units) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(uv[b]) : "l"(ph.x_tagged + u) : "memory");
+        }
+#pragma unroll
+        for (int b = 0; b < UB; ++b) {
+          const int u = u0 + tid + b * TC_CONSUMERS;
+          if (u < n_units) {
+            // (bounded: a protocol bug must show up as a wrong result in the tests, never as a hung GPU)
+            for (int spin = 0; (unsigned)(uv[b] >> 32) != want && spin < (1 << 21); ++spin)
+              asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(uv[b]) : "l"(ph.x_tagged + u) : "memory");
+            const uint32_t v = (uint32_t)uv[b];
+            if (!normed) {
+              *reinterpret_cast<uint32_t*>(xs + 2 * u) = v;
+            } else {
+              const float f0 = bf16lo(v), f1 = bf16hi(v);
+              ss += f0 * f0 + f1 * f1;
+            }
+          }
+        }
+        if (normed) {
+          ss = warp_sum(ss);
+          if (lane == 0) red[warp] = ss;
+          cbar();
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
+          const float rstd = rsqrtf(tot / (float)K + p.eps);
+#pragma unroll
+          for (int b = 0; b < UB; ++b) {
+            const int u = u0 + tid + b * TC_CONSUMERS;
+            if (u < n_units) {
+              const uint32_t v = (uint32_t)uv[b];
+              const uint32_t gw = *reinterpret_cast<const uint32_t*>(xs + 2 * u);
+              *reinterpret_cast<uint32_t*>(xs + 2 * u) = bf16x2_mul(gw, pack_bf16x2(bf16lo(v) * rstd, bf16hi(v) * rstd));
+            }
+          }
+        }
+      }
+      if (tid == 0) trace(i, 1);
       cbar();
     }
     if (tid == 0) trace(i, 2);
@@ -330,6 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
     const bool pairs = (mode == TC_MODE_SWIGLU || mode == TC_MODE_QKV);
     const int R = ng * 16;
     const int n_items = (pairs ? R / 2 : R) * NB;     // item = (row or row pair, clip), clip fastest for NB > 1
+    const unsigned tag_out = (p.n_phases > 1 ? __float_as_uint(red[8]) * 8u : 0u) + (unsigned)i + 1u;
     for (int it0 = 0; it0 < n_items; it0 += TC_CONSUMERS) {       // uniform trip count: the warps stay converged
       const int it = it0 + tid;
       const int b = (NB == 1) ? 0 : it % NB;
@@ -350,7 +403,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
           }
           ph.out[(long long)b * ph.ldo + vrow] = __float2bfloat16_rn(y);
         } else if (mode == TC_MODE_LOGITS) {
-          if (ph.logits != nullptr) ph.logits[(long long)b * ph.ldl + vrow] = bf16r(v0);
+          ph.logits[(long long)b * ph.ldl + vrow] = bf16r(v0);
         } else if (mode == TC_MODE_SWIGLU) {
           const float gt = bf16r(v0);
           const float sg = bf16r(__fdividef(gt, 1.0f + __expf(-gt)));
@@ -361,14 +414,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
           const int which = hr / p.H, head = hr - which * p.H;
           const int d = (vrow & 127) >> 1;
           const float lo = bf16r(v0), hi = bf16r(v1);
-          const int pos = p.pos + (p.pos_dev != nullptr ? __ldg(p.pos_dev) : 0);
-          const long long coff = (((long long)b * p.H + head) * p.s_max + pos) * 128;
+          const long long coff = (((long long)b * p.H + head) * p.s_max + p.pos) * 128;
           if (which == 2) {
             ph.vcache[coff + d] = __float2bfloat16_rn(lo);
             ph.vcache[coff + d + 64] = __float2bfloat16_rn(hi);
           } else {
-            const float cs = __bfloat162float(p.cos_t[(long long)pos * 64 + d]);
-            const float sn = __bfloat162float(p.sin_t[(long long)pos * 64 + d]);
+            const float cs = __bfloat162float(p.cos_t[(long long)p.pos * 64 + d]);
+            const float sn = __bfloat162float(p.sin_t[(long long)p.pos * 64 + d]);
             const float olo = bf16r(lo * cs) + bf16r(-hi * sn);
             const float ohi = bf16r(hi * cs) + bf16r(lo * sn);
             if (which == 0) {
@@ -381,36 +433,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
           }
         }
       }
-    }
-    if (mode == TC_MODE_LOGITS && ph.amax_out != nullptr) {
-      // per-CTA partial arg-max over this CTA's rows (bf16-rounded logits, lowest index wins ties);
-      // the consumer of the partials keeps the lowest index across CTAs as well
-      for (int b = 0; b < NB; ++b) {
-        float bv = -INFINITY; int bi = 0x7fffffff;
-        for (int rr = tid; rr < R; rr += TC_CONSUMERS) {
-          const int vrow = row0 + rr;
-          if (vrow < N) {
-            const float v = bf16r(result[rr * 4 + b]);
-            if (v > bv) { bv = v; bi = vrow; }          // rr ascending: the first maximum is kept
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        cbar();                                          // pbuf is free (and the previous clip's slots read)
-        if (lane == 0) { pbuf[2 * warp] = bv; pbuf[2 * warp + 1] = __int_as_float(bi); }
-        cbar();
-        if (tid == 0) {
-#pragma unroll
-          for (int w = 1; w < TC_CWARPS; ++w) {
-            const float ov = pbuf[2 * w]; const int oi = __float_as_int(pbuf[2 * w + 1]);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-          }
-          ArgmaxPart ap; ap.v = bv; ap.idx = bi;
-          ph.amax_out[(size_t)blockIdx.x * NB + b] = ap;
+      if (ph.out_tagged != nullptr) {
+        // the hand-off copy for the next phase: items (2j, 2j+1) of a warp form one 8-byte unit
+        // {value 2j, value 2j+1, generation}; item k is output element (row0 + k) of RES,
+        // (row0 / 2 + k) of SWIGLU
+        const float y1 = __shfl_down_sync(0xffffffffu, y, 1);
+        if (valid && (it & 1) == 0) {
+          const int elem = (mode == TC_MODE_RES) ? vrow : (vrow >> 1);
+          ph.out_tagged[elem >> 1] = ((unsigned long long)tag_out << 32) | pack_bf16x2(y, y1);
         }
       }
     }
@@ -419,6 +449,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
       if (p.trace != nullptr) p.trace[((size_t)blockIdx.x * TC_MAX_PHASES + i) * 8 + 7] = ((unsigned long long)mode << 32) | (unsigned)N;
     }
   }
+  // next multi-phase launch uses the next generation (it reads the counter after its dependency wait)
+  if (p.n_phases > 1 && blockIdx.x == 0 && tid == 0) *p.gen_counter = __float_as_uint(red[8]) + 1u;
 }
 
 // row-major W[N][K] -> tiled copy. One thread per 16-byte chunk of the output.
@@ -476,14 +508,12 @@ int plan(const TcPhase* ph, int n, int nb, int grid, size_t* smem_bytes, int* x_
 constexpr int TC_TRACE_RECORDS = 512;
 unsigned long long* g_trace = nullptr;
 int g_trace_next = 0;
+unsigned* g_gen = nullptr;            // generation counter of the tagged hand-off buffers (one stream)
 
 TcPhase phase_of(const GemvArgs& g, int mode) {
   TcPhase ph;
   ph.mode = mode; ph.W_tiled = g.W_tiled; ph.N = g.N; ph.K = g.K; ph.x = g.x; ph.norm_w = g.norm_w;
   ph.ring_slots = g.ring_slots; ph.B = g.B; ph.ldx = g.ldx;
-  ph.embed = g.embed; ph.vocab = g.vocab; ph.tok_in = g.tok_in; ph.tok_stride = g.tok_stride;
-  ph.amax_in = g.amax_in; ph.amax_n = g.amax_n; ph.tok_out = g.tok_out; ph.tok_out_stride = g.tok_out_stride;
-  ph.h_out = g.h_out; ph.amax_out = g.amax_out;
   return ph;
 }
 
@@ -494,7 +524,7 @@ bool gemv_tc_chain_supported(const TcPhase* ph, int n) {
   if (off || n < 1 || n > TC_MAX_PHASES) return false;
   for (int i = 0; i < n; ++i) {
     if (ph[i].W_tiled == nullptr || ph[i].N < 16) return false;
-    if ((ph[i].embed == nullptr && ((uintptr_t)ph[i].x % 16) != 0) || ((uintptr_t)ph[i].W_tiled % 16) != 0) return false;
+    if (((uintptr_t)ph[i].x % 16) != 0 || ((uintptr_t)ph[i].W_tiled % 16) != 0) return false;
     if ((ph[i].mode == TC_MODE_SWIGLU || ph[i].mode == TC_MODE_QKV) && ph[i].N % 2 != 0) return false;
   }
   const int nb = ph[0].B;
@@ -509,12 +539,24 @@ int launch_gemv_tc_chain(const TcPhase* ph, int n, const TcChainCommon& c, cudaS
   const int grid = device_num_sms();
   TcParams p = {};
   for (int i = 0; i < n; ++i) p.ph[i] = ph[i];
-  p.n_phases = n; p.eps = c.eps; p.cos_t = c.cos_t; p.sin_t = c.sin_t; p.H = c.H; p.s_max = c.s_max; p.pos = c.pos; p.pos_dev = c.pos_dev;
+  p.n_phases = n; p.eps = c.eps; p.cos_t = c.cos_t; p.sin_t = c.sin_t; p.H = c.H; p.s_max = c.s_max; p.pos = c.pos;
   size_t smem = 0;
   p.nb = ph[0].B;
   VCL_REQUIRE(p.nb >= 1 && p.nb <= 4 && (p.nb == 1 || n == 1), "gemv_tc: %d clips x %d phases not supported", p.nb, n);
   p.n_slots = plan(ph, n, p.nb, grid, &smem, &p.x_elems, &p.r_cap);
   VCL_REQUIRE(p.n_slots >= 4, "gemv_tc: the phases (first N=%d K=%d) do not fit the shared-memory plan", ph[0].N, ph[0].K);
+  if (g_gen == nullptr) {
+    const unsigned one = 1;                          // generation 0 would match zero-initialised buffers
+    VCL_CUDA_OK(cudaMalloc(&g_gen, sizeof(unsigned)));
+    VCL_CUDA_OK(cudaMemcpy(g_gen, &one, sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
+  p.gen_counter = g_gen;
+  for (int i = 1; i < n; ++i) {
+    VCL_REQUIRE(ph[i].norm_w == nullptr || ph[i].K <= 6144, "gemv_tc: fused-norm phase %d with K=%d > 6144", i, ph[i].K);
+    VCL_REQUIRE(ph[i].x_tagged != nullptr && ph[i - 1].out_tagged != nullptr && ph[i - 1].N % 16 == 0 &&
+                    (ph[i - 1].mode == TC_MODE_RES || ph[i - 1].mode == TC_MODE_SWIGLU),
+                "gemv_tc: phase %d needs the tagged output of a residual / SwiGLU phase", i);
+  }
   static const bool tracing = getenv("VCL_TC_TRACE") != nullptr;
   if (tracing) {
     const size_t rec = (size_t)grid * TC_MAX_PHASES * 8;
@@ -596,13 +638,10 @@ int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStrea
 }
 
 int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
-                            const bf16* cos_t, const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream,
-                            const int* pos_dev) {
+                            const bf16* cos_t, const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream) {
   TcPhase ph = phase_of(g, TC_MODE_QKV);
   ph.q_out = q_out; ph.ldq = ldq; ph.kcache = kcache; ph.vcache = vcache;
-  VCL_REQUIRE(g.embed == nullptr || (g.vocab > 0 && (g.tok_in != nullptr || (g.amax_in != nullptr && g.amax_n > 0))),
-              "gemv_tc qkv: the fused embedding gather needs a token source");
-  TcChainCommon c; c.eps = g.eps; c.cos_t = cos_t; c.sin_t = sin_t; c.H = H; c.s_max = s_max; c.pos = pos; c.pos_dev = pos_dev;
+  TcChainCommon c; c.eps = g.eps; c.cos_t = cos_t; c.sin_t = sin_t; c.H = H; c.s_max = s_max; c.pos = pos;
   return launch_gemv_tc_chain(&ph, 1, c, stream);
 }
 

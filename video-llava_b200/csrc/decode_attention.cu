@@ -51,10 +51,14 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scrat
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_cluster_kernel(const bf16* __restrict__ q, long long q_ld, const bf16* __restrict__ kcache,
                            const bf16* __restrict__ vcache, bf16* __restrict__ o, long long o_ld, int H,
-                           int s_max, int kv_len, int per, float scale) {
+                           int s_max, int kv_len, int per_cap, float scale, const int* __restrict__ pos_dev) {
   extern __shared__ float sm[];
-  float* sc = sm;                       // [per] scores -> probabilities of my keys
-  float* red = sm + per;                // [16][128] partial outputs over the 16 key groups
+  float* sc = sm;                       // [per_cap] scores -> probabilities of my keys
+  float* red = sm + per_cap;            // [16][128] partial outputs over the 16 key groups
+  // the number of cached keys may live on the device (one captured graph for every prompt length);
+  // it is constant while the graph runs, so it can be read before the dependency wait
+  if (pos_dev != nullptr) kv_len += __ldg(pos_dev);
+  const int per = ((kv_len + DA_SPLIT - 1) / DA_SPLIT + 15) / 16 * 16;   // keys per CTA, multiple of 16
   float* outp = red + 16 * 128;         // [128] this CTA's partial output
   float* stat = outp + 128;             // [0] local max, [1] local sum
   float* scratch = stat + 2;            // [8]
@@ -172,10 +176,12 @@ decode_attn_cluster_kernel(const bf16* __restrict__ q, long long q_ld, const bf1
 
 int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, const bf16* vcache,
                             bf16* o, long long o_ld, int B, int H, int head_dim, int s_max,
-                            int kv_len, float scale, cudaStream_t stream) {
+                            int kv_len, float scale, cudaStream_t stream, const int* pos_dev) {
   VCL_REQUIRE(head_dim == 128, "decode attention: head_dim must be 128");
   VCL_REQUIRE(kv_len > 0 && kv_len <= s_max, "decode attention: kv_len %d out of range", kv_len);
-  const int per = ((kv_len + DA_SPLIT - 1) / DA_SPLIT + 15) / 16 * 16;   // keys per CTA, multiple of 16
+  // shared memory is sized for the longest sequence when the length is only known on the device
+  const int kv_cap = pos_dev != nullptr ? s_max : kv_len;
+  const int per = ((kv_cap + DA_SPLIT - 1) / DA_SPLIT + 15) / 16 * 16;
   const size_t smem = (size_t)(per + 16 * 128 + 128 + 2 + 8) * sizeof(float);
   VCL_REQUIRE(smem <= 48 * 1024, "decode attention: kv_len %d too long for the smem budget", kv_len);
   cudaLaunchConfig_t cfg = {};
@@ -193,7 +199,7 @@ int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, c
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_attn_cluster_kernel, q, q_ld, kcache, vcache, o, o_ld, H,
-                                 s_max, kv_len, per, scale));
+                                 s_max, kv_len, per, scale, pos_dev));
   count_launches(1);
   return 0;
 }

@@ -253,9 +253,11 @@ embed_splice_kernel(const long long* __restrict__ ids, const bf16* __restrict__ 
                     bf16* __restrict__ h, int S, int D, int n_vid, int vocab) {
   const long long row = blockIdx.x;
   const int b = (int)(row / S), s = (int)(row % S);
-  const int vs = vid_start != nullptr ? vid_start[b] : -1;   // null: text-only rows (prefill continuation)
+  // vid_start[b] = index of the row AFTER which the video rows go (-1: the video rows start at row 0);
+  // anything below -1 (VCL_NO_VIDEO), or a null array, marks a text-only row
+  const int vs = vid_start != nullptr ? vid_start[b] : -2;
   const bf16* src;
-  if (vs >= 0 && s > vs && s <= vs + n_vid) {
+  if (vs >= -1 && s > vs && s <= vs + n_vid) {
     src = vid + ((long long)b * n_vid + (s - vs - 1)) * D;
   } else {
     long long id = ids[row];
@@ -296,7 +298,7 @@ __global__ void rope_table_kernel(bf16* cos_t, bf16* sin_t, int max_pos, int hea
 __global__ void __launch_bounds__(256)
 rope_kv_prefill_kernel(bf16* qkv, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
                        const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t, int B, int S,
-                       int H, int s_max, int pos0) {
+                       int H, int s_max, int pos0, const int* __restrict__ pos_dev) {
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (wid >= (long long)B * S * H) return;
@@ -305,7 +307,7 @@ rope_kv_prefill_kernel(bf16* qkv, bf16* __restrict__ kcache, bf16* __restrict__ 
   const int b = (int)(tok / S), s = (int)(tok % S);
   const int D = H * 128;
   bf16* row = qkv + tok * 3LL * D;
-  const int pos = pos0 + s;
+  const int pos = pos0 + s + (pos_dev != nullptr ? __ldg(pos_dev) : 0);
   const long long cache_off = (((long long)b * H + head) * s_max + pos) * 128;
   if (lane < 16) {
     const int which = lane >> 3;              // 0 = q, 1 = k
@@ -461,13 +463,22 @@ int launch_rope_table(bf16* cos_t, bf16* sin_t, int max_pos, int head_dim, float
 
 int launch_rope_kv_prefill(bf16* qkv, bf16* kcache, bf16* vcache, const bf16* cos_t,
                            const bf16* sin_t, int B, int S, int H, int head_dim, int s_max, int pos0,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const int* pos_dev) {
   VCL_REQUIRE(head_dim == 128, "rope: head_dim must be 128 (got %d)", head_dim);
   VCL_REQUIRE(pos0 + S <= s_max, "rope: positions %d..%d exceed the cache (%d)", pos0, pos0 + S, s_max);
   const long long warps = (long long)B * S * H;
   if (warps <= 0) return 0;
   rope_kv_prefill_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(qkv, kcache, vcache, cos_t,
-                                                                        sin_t, B, S, H, s_max, pos0);
+                                                                        sin_t, B, S, H, s_max, pos0, pos_dev);
+  VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
+  return 0;
+}
+
+__global__ void set_int_kernel(int* dst, int value) { *dst = value; }
+
+int launch_set_int(int* dst, int value, cudaStream_t stream) {
+  set_int_kernel<<<1, 1, 0, stream>>>(dst, value);
   VCL_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return 0;

@@ -55,6 +55,7 @@ struct GemvParams {
   bf16* kcache; bf16* vcache;
   const bf16* cos_t; const bf16* sin_t;
   int H, s_max, pos;
+  const int* pos_dev;
   // LOGITS
   float* logits; long long ldl;
 };
@@ -252,13 +253,14 @@ __global__ void __launch_bounds__(GEMV_THREADS, (NB * J <= 4) ? 2 : 1) gemv_kern
       const int which = hr / p.H, head = hr - which * p.H;
       const int d = (vrow & 127) >> 1;
       const float lo = bf16r(v0), hi = bf16r(v1);
-      const long long coff = (((long long)b * p.H + head) * p.s_max + p.pos) * 128;
+      const int pos = p.pos + (p.pos_dev != nullptr ? __ldg(p.pos_dev) : 0);
+      const long long coff = (((long long)b * p.H + head) * p.s_max + pos) * 128;
       if (which == 2) {
         p.vcache[coff + d] = __float2bfloat16_rn(lo);
         p.vcache[coff + d + 64] = __float2bfloat16_rn(hi);
       } else {
-        const float c = __bfloat162float(p.cos_t[(long long)p.pos * 64 + d]);
-        const float s = __bfloat162float(p.sin_t[(long long)p.pos * 64 + d]);
+        const float c = __bfloat162float(p.cos_t[(long long)pos * 64 + d]);
+        const float s = __bfloat162float(p.sin_t[(long long)pos * 64 + d]);
         const float olo = bf16r(lo * c) + bf16r(-hi * s);
         const float ohi = bf16r(hi * c) + bf16r(lo * s);
         if (which == 0) {
@@ -377,15 +379,16 @@ int launch_gemv_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t
 
 int launch_gemv_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
                          const bf16* cos_t, const bf16* sin_t, int H, int head_dim, int s_max,
-                         int pos, cudaStream_t stream) {
+                         int pos, cudaStream_t stream, const int* pos_dev) {
   VCL_REQUIRE(head_dim == 128, "gemv qkv: head_dim must be 128");
   VCL_REQUIRE(g.N == 3 * H * 128, "gemv qkv: N=%d != 3*H*128", g.N);
   VCL_REQUIRE(pos >= 0 && pos < s_max, "gemv qkv: position %d outside the cache (%d)", pos, s_max);
   if (gemv_tc_supported(g))
-    return launch_gemv_tc_qkv_rope(g, q_out, ldq, kcache, vcache, cos_t, sin_t, H, s_max, pos, stream);
+    return launch_gemv_tc_qkv_rope(g, q_out, ldq, kcache, vcache, cos_t, sin_t, H, s_max, pos, stream, pos_dev);
+  VCL_REQUIRE(g.embed == nullptr, "gemv qkv: the fused embedding gather needs the ring kernel (gemv_tc)");
   GemvParams p = base_params(g);
   p.q_out = q_out; p.ldq = ldq; p.kcache = kcache; p.vcache = vcache;
-  p.cos_t = cos_t; p.sin_t = sin_t; p.H = H; p.s_max = s_max; p.pos = pos;
+  p.cos_t = cos_t; p.sin_t = sin_t; p.H = H; p.s_max = s_max; p.pos = pos; p.pos_dev = pos_dev;
   return launch_mode<MODE_QKV>(g.B, p, stream);
 }
 

@@ -41,6 +41,7 @@ struct GmParams {
   bf16* kcache; bf16* vcache;
   const bf16* cos_t; const bf16* sin_t;
   int H, s_max, pos;
+  const int* pos_dev;
   float* logits; long long ldl;
 };
 
@@ -161,13 +162,14 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemv_mma_kernel(const GmParams 
       const int which = hr / p.H, head = hr - which * p.H;
       const int d = (vrow & 127) >> 1;
       const float lo = bf16r(v0), hi = bf16r(v1);
-      const long long coff = (((long long)b * p.H + head) * p.s_max + p.pos) * 128;
+      const int pos = p.pos + (p.pos_dev != nullptr ? __ldg(p.pos_dev) : 0);
+      const long long coff = (((long long)b * p.H + head) * p.s_max + pos) * 128;
       if (which == 2) {
         p.vcache[coff + d] = __float2bfloat16_rn(lo);
         p.vcache[coff + d + 64] = __float2bfloat16_rn(hi);
       } else {
-        const float cs = __bfloat162float(p.cos_t[(long long)p.pos * 64 + d]);
-        const float sn = __bfloat162float(p.sin_t[(long long)p.pos * 64 + d]);
+        const float cs = __bfloat162float(p.cos_t[(long long)pos * 64 + d]);
+        const float sn = __bfloat162float(p.sin_t[(long long)pos * 64 + d]);
         const float olo = bf16r(lo * cs) + bf16r(-hi * sn);
         const float ohi = bf16r(hi * cs) + bf16r(lo * sn);
         if (which == 0) {
@@ -250,12 +252,12 @@ int launch_gemv_mma_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStre
 
 int launch_gemv_mma_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
                              const bf16* cos_t, const bf16* sin_t, int H, int head_dim, int s_max, int pos,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const int* pos_dev) {
   VCL_REQUIRE(g.norm_w == nullptr && head_dim == 128 && g.N == 3 * H * 128, "gemv_mma qkv: bad arguments");
   VCL_REQUIRE(pos >= 0 && pos < s_max, "gemv_mma qkv: position %d outside the cache (%d)", pos, s_max);
   GmParams p = gm_base(g);
   p.q_out = q_out; p.ldq = ldq; p.kcache = kcache; p.vcache = vcache;
-  p.cos_t = cos_t; p.sin_t = sin_t; p.H = H; p.s_max = s_max; p.pos = pos;
+  p.cos_t = cos_t; p.sin_t = sin_t; p.H = H; p.s_max = s_max; p.pos = pos; p.pos_dev = pos_dev;
   return gm_dispatch<MODE_QKV>(p, stream);
 }
 

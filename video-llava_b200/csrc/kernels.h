@@ -59,14 +59,17 @@ int launch_embed_splice(const long long* ids, const bf16* table, const bf16* vid
 int launch_rope_table(bf16* cos_t, bf16* sin_t, int max_pos, int head_dim, float theta,
                       cudaStream_t stream);
 // prefill: rotate q (in place inside qkv) and k, write k/v into the cache at [pos0, pos0+S)
+// (pos_dev != null: the position is pos0 + *pos_dev, read on the device -- a captured decode graph then
+// serves every prompt length; the same convention holds for every `pos_dev` below)
 int launch_rope_kv_prefill(bf16* qkv, bf16* kcache, bf16* vcache, const bf16* cos_t,
                            const bf16* sin_t, int B, int S, int H, int head_dim, int s_max, int pos0,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const int* pos_dev = nullptr);
 // h[b,:] = table[tok[b*tok_stride]]  (decode-time embedding lookup, tokens live on the device)
 int launch_embed_tokens(const int* tok, long long tok_stride, const bf16* table, bf16* h, int B,
                         int D, int vocab, cudaStream_t stream);
 int launch_argmax(const float* logits, int* out, long long out_stride, int B, int V,
                   cudaStream_t stream);
+int launch_set_int(int* dst, int value, cudaStream_t stream);
 
 // ---- st_pool.cu ---------------------------------------------------------------------------------
 // dtype codes: 0 = fp16, 1 = bf16
@@ -97,33 +100,13 @@ int init_attention_tc_kernels();
 // single-query attention against the cache: q [B, H*hd] -> o [B, H*hd]; kv_len keys per clip
 int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, const bf16* vcache,
                             bf16* o, long long o_ld, int B, int H, int head_dim, int s_max,
-                            int kv_len, float scale, cudaStream_t stream);
-
-// ---- decode_mega.cu : one whole cached decoding step (B <= 4) as a single persistent kernel ------
-struct MegaLayer { const bf16 *ln1, *wqkv, *wo, *ln2, *wgu, *wd; };
-struct MegaParams {
-  int L, D, F, H, V, s_max;
-  float eps, scale;
-  const MegaLayer* layers;          // device array [L]
-  const bf16 *embed, *norm_w, *lm_head;
-  bf16 *kcache, *vcache;            // [L][B][H][s_max][128]
-  long long cache_layer_elems;
-  const bf16 *cos_t, *sin_t;
-  bf16 *h, *q, *act;                // [B,D], [B,D], [B,F]
-  float *att_stats, *att_part;      // [B,H,4,2], [B,H,4,128]
-  float* logits;                    // [B,V]
-  const int* tok_in; long long tok_in_stride;
-  int* tok_out; long long tok_out_stride;
-  int pos;
-  unsigned int* barrier;            // grid-barrier counter (zeroed by the launcher)
-  int l2_slots;                     // fills of L2 prefetch kept ahead of the shared-memory ring
-  unsigned long long* trace;        // optional per-CTA phase timestamps (VCL_MEGA_TRACE), else nullptr
-};
-int init_decode_mega_kernels();
-bool decode_mega_supported(int B, int D, int F, int V);
-int launch_decode_mega(const MegaParams& p, int B, cudaStream_t stream);
+                            int kv_len, float scale, cudaStream_t stream, const int* pos_dev = nullptr);
 
 // ---- gemv.cu : decode-time weight streaming (M = B <= 8 rows) ------------------------------------
+// per-CTA partial arg-max of the logits kernel: the next step's q|k|v kernel reduces the grid's
+// partials itself (lowest index wins ties), so no arg-max kernel runs between two decode steps
+struct ArgmaxPart { float v; int idx; };
+
 struct GemvArgs {
   const bf16* x = nullptr; long long ldx = 0;   // [B, K]
   const bf16* W = nullptr;                      // [N, K]
@@ -131,6 +114,16 @@ struct GemvArgs {
   int ring_slots = 0;                           // gemv_tc: deeper shared-memory ring than the default (0 = default)
   int B = 0, N = 0, K = 0;
   const bf16* norm_w = nullptr; float eps = 0;  // optional fused RMSNorm prologue
+  // gemv_tc only. q|k|v with a fused token-embedding gather: x is row `token` of `embed` [vocab, K],
+  // the token read from tok_in[b * tok_stride] or reduced from the previous step's arg-max partials
+  // (amax_in [amax_n][B]); CTA 0 then stores the token (tok_out) and the raw row (h_out [B][K], the
+  // residual stream). Logits: amax_out [grid][B] receives the per-CTA partial arg-max.
+  const bf16* embed = nullptr; int vocab = 0;
+  const int* tok_in = nullptr; long long tok_stride = 0;
+  const ArgmaxPart* amax_in = nullptr; int amax_n = 0;
+  int* tok_out = nullptr; long long tok_out_stride = 0;
+  bf16* h_out = nullptr;
+  ArgmaxPart* amax_out = nullptr;
 };
 // out[b, n] = bf16(bf16(x.W[n]) + res[b, n])      (res may alias out; res == null -> plain)
 int launch_gemv_residual(const GemvArgs& g, bf16* out, long long ldo, const bf16* res,
@@ -140,15 +133,12 @@ int launch_gemv_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t
 // fused q/k/v projection + RoPE + cache write for one new token per clip at position pos
 int launch_gemv_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
                          const bf16* cos_t, const bf16* sin_t, int H, int head_dim, int s_max,
-                         int pos, cudaStream_t stream);
+                         int pos, cudaStream_t stream, const int* pos_dev = nullptr);
 int init_gemv_kernels();
 
 // ---- gemv_tc.cu : 1..4 clips (bulk-copy ring over a slot-ordered weight copy + mma.sync) ---------
 // The launch_gemv_* entry points above route to these when gemv_tc_supported(g).
 int init_gemv_tc_kernels();
-// One launch can run up to 4 DEPENDENT projections back to back (o_proj -> gate/up -> down -> next
-// layer's q/k/v): the producer warp streams the weights of all phases without waiting, the consumers
-// separate the phases with a grid barrier, so HBM does not idle at those boundaries.
 enum { TC_MODE_RES = 0, TC_MODE_SWIGLU = 1, TC_MODE_QKV = 2, TC_MODE_LOGITS = 3 };
 struct TcPhase {
   int mode = TC_MODE_RES;
@@ -161,16 +151,20 @@ struct TcPhase {
   const bf16* res = nullptr; long long ldr = 0;
   bf16* q_out = nullptr; long long ldq = 0;          // QKV: q [B][ldq], cache base of the layer [B][H][S][128]
   bf16* kcache = nullptr; bf16* vcache = nullptr;
-  float* logits = nullptr; long long ldl = 0;        // LOGITS: [B][ldl] bf16-rounded fp32
-  // hand-off between the phases of one launch: the same vector as `out` / `x`, as 8-byte units
-  // {bf16, bf16, u32 generation} (see gemv_tc.cu); x_tagged is read by every phase but the first
-  unsigned long long* out_tagged = nullptr;
-  const unsigned long long* x_tagged = nullptr;
+  float* logits = nullptr; long long ldl = 0;        // LOGITS: [B][ldl] bf16-rounded fp32 (null: not stored)
+  ArgmaxPart* amax_out = nullptr;                    // LOGITS: [grid][B] per-CTA partial arg-max
+  // QKV with a fused embedding gather (see GemvArgs)
+  const bf16* embed = nullptr; int vocab = 0;
+  const int* tok_in = nullptr; long long tok_stride = 0;
+  const ArgmaxPart* amax_in = nullptr; int amax_n = 0;
+  int* tok_out = nullptr; long long tok_out_stride = 0;
+  bf16* h_out = nullptr;
 };
 struct TcChainCommon {
   float eps = 0.f;
   const bf16* cos_t = nullptr; const bf16* sin_t = nullptr;
   int H = 0, s_max = 0, pos = 0;
+  const int* pos_dev = nullptr;                      // position = pos + *pos_dev
 };
 bool gemv_tc_chain_supported(const TcPhase* ph, int n);
 int launch_gemv_tc_chain(const TcPhase* ph, int n, const TcChainCommon& c, cudaStream_t stream);
@@ -182,7 +176,8 @@ int launch_gemv_tc_residual(const GemvArgs& g, bf16* out, long long ldo, const b
                             cudaStream_t stream);
 int launch_gemv_tc_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t stream);
 int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
-                            const bf16* cos_t, const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream);
+                            const bf16* cos_t, const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream,
+                            const int* pos_dev = nullptr);
 int launch_gemv_tc_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
 // logits (bf16-rounded, stored fp32) [B, N]
 int launch_gemv_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
@@ -194,7 +189,7 @@ int launch_gemv_mma_residual(const GemvArgs& g, bf16* out, long long ldo, const 
 int launch_gemv_mma_swiglu(const GemvArgs& g, bf16* out, long long ldo, cudaStream_t stream);
 int launch_gemv_mma_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
                              const bf16* cos_t, const bf16* sin_t, int H, int head_dim, int s_max, int pos,
-                             cudaStream_t stream);
+                             cudaStream_t stream, const int* pos_dev = nullptr);
 int launch_gemv_mma_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
 
 

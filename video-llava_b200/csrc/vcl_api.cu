@@ -49,9 +49,22 @@ struct LlmLayerW {
   bf16 *wqkv_t = nullptr, *wo_t = nullptr, *wgu_t = nullptr, *wd_t = nullptr;   // tiled copies for B = 1 decode
 };
 struct GraphEntry {
-  int B, S, n_new;
+  int B, S, n_new;     // S = -1: the prompt length is read on the device (h->d_pos), any S replays it
   cudaGraphExec_t exec;
   long long kernels;   // kernel nodes in the graph (for vcl_launch_count)
+  unsigned long long last_use;
+};
+constexpr size_t MAX_DECODE_GRAPHS = 6;   // LRU-bounded: an instantiated graph holds ~5 000 kernel nodes
+
+// what one decode step reads and leaves behind
+struct StepIo {
+  const int32_t* tok_in = nullptr; long long in_stride = 1;      // the token fed at this step ...
+  bool tok_from_partials = false;                                // ... or: the arg-max of the previous step's partials
+  int32_t* tok_store = nullptr; long long store_stride = 1;      // where that reduced token is recorded
+  bool partials_out = false;      // leave this step's arg-max as per-CTA partials for the next step (no arg-max kernel)
+  float* logits_out = nullptr;
+  int32_t* tok_out = nullptr; long long out_stride = 1;
+  const int* pos_dev = nullptr;   // position = pos + *pos_dev
 };
 
 }  // namespace
@@ -83,11 +96,9 @@ struct vcl_handle {
   bf16 *d_h = nullptr, *d_x = nullptr, *d_q = nullptr, *d_qkv = nullptr, *d_attn = nullptr,
        *d_act = nullptr;
   std::vector<GraphEntry> graphs;
-  MegaLayer* mega_layers = nullptr;            // device copy of the per-layer weight pointers
-  float *att_stats = nullptr, *att_part = nullptr;
-  unsigned int* mega_barrier = nullptr;
-  unsigned long long *h_tag = nullptr, *act_tag = nullptr;   // tagged hand-off copies of d_h / d_act (gemv_tc chains)
-  bool use_mega = false;     // VCL_MEGAKERNEL=1: one persistent kernel per decode step (slower, kept for study)
+  unsigned long long graph_clock = 0;
+  int* d_pos = nullptr;                        // prompt length of the running decode loop (device scalar)
+  ArgmaxPart* amax = nullptr;                  // [#SMs][max_batch] per-CTA partial arg-max of the logits kernel
   bool force_legacy_attention = false;
 
   size_t cache_layer_elems() const {
@@ -195,9 +206,6 @@ int vcl_create(vcl_handle** out, const vcl_config* c) {
   rc |= init_gemm_kernels();
   rc |= init_attention_kernels();
   rc |= init_attention_tc_kernels();
-  rc |= init_decode_mega_kernels();
-  // the persistent whole-step kernel is correct but (round 1) slower than the per-phase GEMV chain: opt-in
-  h->use_mega = getenv("VCL_MEGAKERNEL") != nullptr && getenv("VCL_NO_MEGAKERNEL") == nullptr;
   h->force_legacy_attention = getenv("VCL_LEGACY_ATTENTION") != nullptr;
   rc |= init_gemv_kernels();
   rc |= init_gemv_tc_kernels();
@@ -235,16 +243,8 @@ int vcl_create(vcl_handle** out, const vcl_config* c) {
   rc |= dalloc(h, &h->d_qkv, Bm * 3 * D);
   rc |= dalloc(h, &h->d_attn, Bm * D);
   rc |= dalloc(h, &h->d_act, Bm * LF);
-  rc |= dalloc(h, &h->att_stats, Bm * c->llm_heads * 4 * 2);
-  rc |= dalloc(h, &h->att_part, Bm * c->llm_heads * 4 * 128);
-  rc |= dalloc(h, &h->mega_barrier, 32 * 17);
-  rc |= dalloc(h, &h->h_tag, (size_t)c->llm_hidden / 2 + 8);
-  rc |= dalloc(h, &h->act_tag, (size_t)c->llm_inter / 2 + 8);
-  if (rc == 0) {
-    cudaMemset(h->h_tag, 0, ((size_t)c->llm_hidden / 2 + 8) * 8);
-    cudaMemset(h->act_tag, 0, ((size_t)c->llm_inter / 2 + 8) * 8);
-  }
-  rc |= dalloc(h, &h->mega_layers, (size_t)(c->llm_layers > 0 ? c->llm_layers : 1));
+  rc |= dalloc(h, &h->d_pos, 4);
+  rc |= dalloc(h, &h->amax, (size_t)device_num_sms() * Bm);
   if (rc == 0) rc = launch_rope_table(h->rope_cos, h->rope_sin, c->max_seq, 128, c->rope_theta, 0);
   if (rc == 0) {
     cudaError_t e = cudaDeviceSynchronize();
@@ -379,15 +379,6 @@ int vcl_load_llm_weights(vcl_handle* h, const vcl_tensor* tensors, int n) {
     }
     if (tiled(h->lm_head, &h->lm_head_t, V, D, false)) return -2;
   }
-  {
-    std::vector<MegaLayer> ml(c.llm_layers);
-    for (int l = 0; l < c.llm_layers; ++l) {
-      const LlmLayerW& w = h->ll[l];
-      ml[l] = MegaLayer{w.ln1, w.wqkv, w.wo, w.ln2, w.wgu, w.wd};
-    }
-    if (c.llm_layers > 0)
-      VCL_CUDA_OK(cudaMemcpy(h->mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
-  }
   VCL_CUDA_OK(cudaDeviceSynchronize());
   h->llm_loaded = true;
   return 0;
@@ -460,10 +451,10 @@ int clip_forward(vcl_handle* h, const void* pixels, int fmt, int n_frames, int n
 bf16* kc_layer(vcl_handle* h, int l) { return h->kcache + (size_t)l * h->cache_layer_elems(); }
 bf16* vc_layer(vcl_handle* h, int l) { return h->vcache + (size_t)l * h->cache_layer_elems(); }
 
-// 2..4 clips can take the single-clip kernel family (gemv_tc, activation vectors of all clips in shared
-// memory) when every projection of the model fits its shared-memory plan; 5..16 clips use gemv_mma
-static bool tc_small_batch(vcl_handle* h, int B) {
-  if (B < 2 || B > 4 || h->lm_head_t == nullptr || h->ll.empty()) return false;
+// 1..4 clips take the ring-kernel family (gemv_tc, activation vectors of all clips in shared memory)
+// when every projection of the model fits its shared-memory plan; 5..16 clips use gemv_mma
+static bool tc_batch(vcl_handle* h, int B) {
+  if (B < 1 || B > 4 || h->lm_head_t == nullptr || h->ll.empty()) return false;
   const vcl_config& c = h->cfg;
   const int D = c.llm_hidden, F = c.llm_inter;
   const int shapes[5][2] = {{3 * D, D}, {D, D}, {2 * F, D}, {D, F}, {c.vocab, D}};
@@ -476,10 +467,17 @@ static bool tc_small_batch(vcl_handle* h, int B) {
 }
 
 // final RMSNorm + lm_head on rows x[b*ldx .. ] (b < B), arg-max
+// partials_out: the arg-max is left as per-CTA partials in h->amax for the next step's q|k|v kernel
 int lm_head_argmax(vcl_handle* h, const bf16* x, long long ldx, int B, float* logits_out,
-                   int32_t* tok_out, long long tok_stride, cudaStream_t st) {
+                   int32_t* tok_out, long long tok_stride, cudaStream_t st, bool partials_out = false) {
   const vcl_config& c = h->cfg;
-  if (B >= 2 && !tc_small_batch(h, B)) {
+  if (partials_out) {
+    GemvArgs g;
+    g.x = x; g.ldx = ldx; g.W = h->lm_head; g.W_tiled = h->lm_head_t; g.B = B; g.N = c.vocab;
+    g.K = c.llm_hidden; g.norm_w = h->norm_w; g.eps = c.rms_eps; g.amax_out = h->amax;
+    return launch_gemv_tc_logits(g, nullptr, c.vocab, st);
+  }
+  if (B >= 2 && !tc_batch(h, B)) {
     // small batches: normalise the B rows once, then the mma.sync weight-streaming kernel
     for (int b0 = 0; b0 < B; b0 += 16) {
       const int nb = B - b0 < 16 ? B - b0 : 16;
@@ -506,9 +504,11 @@ int lm_head_argmax(vcl_handle* h, const bf16* x, long long ldx, int B, float* lo
 
 // start_pos > 0 continues a cached sequence: the S new tokens take positions start_pos .. start_pos+S-1
 // and attend to the whole cache (multi-turn reuse; no video span in a continuation).
+// states_out (optional): [n_layers + 1][B][S][D], entry i = HF's hidden_states[i] (the raw output of
+// layer i; entry 0 the spliced input embeddings), copied out as the stack advances.
 int llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats, const int32_t* vid_start,
                 int B, int S, int n_layers, void* hidden_out, float* logits_out, int32_t* next_tok,
-                long long tok_stride, cudaStream_t st, int start_pos = 0) {
+                long long tok_stride, cudaStream_t st, int start_pos = 0, void* states_out = nullptr) {
   const vcl_config& c = h->cfg;
   VCL_REQUIRE(h->llm_loaded, "LLM weights are not loaded");
   VCL_REQUIRE(B > 0 && B <= c.max_batch, "B=%d outside 1..%d", B, c.max_batch);
@@ -536,6 +536,13 @@ int llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats, cons
   VCL_TRY(launch_embed_splice(reinterpret_cast<const long long*>(ids), h->embed, h->l_vid, vid_start,
                               h->l_h, B, S, D, video_feats ? NV : 0, c.vocab, st));
   const float scale = 0.08838834764831845f;  // 128 ^ -1/2
+  auto keep_state = [&](int i) -> int {
+    if (states_out == nullptr) return 0;
+    VCL_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<bf16*>(states_out) + (size_t)i * M * D, h->l_h, (size_t)M * D * 2,
+                                cudaMemcpyDeviceToDevice, st));
+    return 0;
+  };
+  VCL_TRY(keep_state(0));
   for (int l = 0; l < n_layers; ++l) {
     const LlmLayerW& w = h->ll[l];
     VCL_TRY(launch_rmsnorm(h->l_h, D, h->l_x, D, w.ln1, M, D, c.rms_eps, st));
@@ -554,6 +561,7 @@ int llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats, cons
     VCL_TRY(launch_rmsnorm(h->l_h, D, h->l_x, D, w.ln2, M, D, c.rms_eps, st));
     VCL_TRY(gemm(h->l_x, D, w.wgu, D, h->l_act, F, nullptr, nullptr, 0, M, 2 * F, D, ACT_SWIGLU, st));
     VCL_TRY(gemm(h->l_act, F, w.wd, F, h->l_h, D, nullptr, h->l_h, D, M, D, F, ACT_NONE, st));
+    VCL_TRY(keep_state(l + 1));
   }
   if (hidden_out != nullptr)
     VCL_CUDA_OK(cudaMemcpyAsync(hidden_out, h->l_h, (size_t)M * D * 2, cudaMemcpyDeviceToDevice, st));
@@ -563,101 +571,29 @@ int llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats, cons
   return 0;
 }
 
-// One decode step. tok_in[b * in_stride] is fed at position pos; result to tok_out[b * out_stride].
-int llm_decode_step(vcl_handle* h, const int32_t* tok_in, long long in_stride, int B, int pos,
-                    float* logits_out, int32_t* tok_out, long long out_stride, cudaStream_t st) {
+// One decode step: the token of io is fed at position pos (+ *io.pos_dev).
+int llm_decode_step(vcl_handle* h, const StepIo& io, int B, int pos, cudaStream_t st) {
   const vcl_config& c = h->cfg;
   const int D = c.llm_hidden, F = c.llm_inter, H = c.llm_heads;
   const float scale = 0.08838834764831845f;
+  const int* pd = io.pos_dev;
   VCL_REQUIRE(pos >= 0 && pos < c.max_seq, "decode position %d outside the cache (max_seq %d)", pos, c.max_seq);
-  if (h->use_mega && tok_out != nullptr && c.llm_layers > 0 && decode_mega_supported(B, D, F, c.vocab) &&
-      pos + 1 <= 512 && B * H * 4 <= 4 * device_num_sms()) {
-    MegaParams mp = {};
-    mp.L = c.llm_layers; mp.D = D; mp.F = F; mp.H = H; mp.V = c.vocab; mp.s_max = c.max_seq;
-    mp.eps = c.rms_eps; mp.scale = scale;
-    mp.layers = h->mega_layers; mp.embed = h->embed; mp.norm_w = h->norm_w; mp.lm_head = h->lm_head;
-    mp.kcache = h->kcache; mp.vcache = h->vcache; mp.cache_layer_elems = (long long)h->cache_layer_elems();
-    mp.cos_t = h->rope_cos; mp.sin_t = h->rope_sin;
-    mp.h = h->d_h; mp.q = h->d_q; mp.act = h->d_act;
-    mp.att_stats = h->att_stats; mp.att_part = h->att_part; mp.logits = h->logits;
-    mp.tok_in = tok_in; mp.tok_in_stride = in_stride; mp.tok_out = tok_out; mp.tok_out_stride = out_stride;
-    mp.pos = pos; mp.barrier = h->mega_barrier;
-    VCL_TRY(launch_decode_mega(mp, B, st));
-    if (logits_out != nullptr && logits_out != h->logits)
-      VCL_CUDA_OK(cudaMemcpyAsync(logits_out, h->logits, (size_t)B * c.vocab * sizeof(float),
-                                  cudaMemcpyDeviceToDevice, st));
-    return 0;
-  }
-  VCL_TRY(launch_embed_tokens(tok_in, in_stride, h->embed, h->d_h, B, D, c.vocab, st));
-  // Opt-in experiment (VCL_DECODE_FUSED=1), single clip: two launches per layer. [q|k|v] -> attention ->
-  // [o_proj, gate/up, down, next layer's q|k|v (or the LM head)] ... : the dependent projections
-  // between two attention kernels run as phases of ONE gemv_tc launch with an in-kernel hand-off.
-  // Parity-green, but 8 % slower than one launch per projection (82 vs 74 ms per 31 steps): a
-  // programmatic dependent launch releases the next kernel ~1 us after the last CTA is done, the
-  // cheapest in-kernel hand-off measured (tagged 8-byte units, no fences) needs ~3 us, and the next
-  // kernel's ring is pre-filled in both cases. See profiles/r01_tc_trace.txt.
-  if (B == 1 && c.llm_layers > 0 && h->lm_head_t != nullptr && getenv("VCL_DECODE_FUSED") != nullptr) {
-    TcChainCommon cc;
-    cc.eps = c.rms_eps; cc.cos_t = h->rope_cos; cc.sin_t = h->rope_sin; cc.H = H; cc.s_max = c.max_seq; cc.pos = pos;
-    auto qkv_phase = [&](int l) {
-      TcPhase ph;
-      ph.mode = TC_MODE_QKV; ph.W_tiled = h->ll[l].wqkv_t; ph.N = 3 * D; ph.K = D; ph.x = h->d_h; ph.norm_w = h->ll[l].ln1;
-      ph.q_out = h->d_q; ph.kcache = kc_layer(h, l); ph.vcache = vc_layer(h, l);
-      return ph;
-    };
-    TcPhase chain[4];
-    chain[0] = qkv_phase(0);
-    bool ok = gemv_tc_chain_supported(chain, 1);
-    {
-      const LlmLayerW& w = h->ll[0];
-      chain[0].mode = TC_MODE_RES; chain[0].W_tiled = w.wo_t; chain[0].N = D; chain[0].K = D; chain[0].x = h->d_attn;
-      chain[0].norm_w = nullptr; chain[0].out = h->d_h; chain[0].res = h->d_h; chain[0].out_tagged = h->h_tag;
-      chain[1] = TcPhase(); chain[1].mode = TC_MODE_SWIGLU; chain[1].W_tiled = w.wgu_t; chain[1].N = 2 * F; chain[1].K = D;
-      chain[1].x = h->d_h; chain[1].x_tagged = h->h_tag; chain[1].norm_w = w.ln2; chain[1].out = h->d_act; chain[1].out_tagged = h->act_tag;
-      chain[2] = TcPhase(); chain[2].mode = TC_MODE_RES; chain[2].W_tiled = w.wd_t; chain[2].N = D; chain[2].K = F;
-      chain[2].x = h->d_act; chain[2].x_tagged = h->act_tag; chain[2].out = h->d_h; chain[2].res = h->d_h; chain[2].out_tagged = h->h_tag;
-      chain[3] = TcPhase(); chain[3].mode = TC_MODE_LOGITS; chain[3].W_tiled = h->lm_head_t; chain[3].N = c.vocab; chain[3].K = D;
-      chain[3].x = h->d_h; chain[3].x_tagged = h->h_tag; chain[3].norm_w = h->norm_w; chain[3].logits = h->logits;
-      ok = ok && gemv_tc_chain_supported(chain, 4);
-    }
-    if (ok) {
-      TcPhase first = qkv_phase(0);
-      VCL_TRY(launch_gemv_tc_chain(&first, 1, cc, st));
-      for (int l = 0; l < c.llm_layers; ++l) {
-        const LlmLayerW& w = h->ll[l];
-        VCL_TRY(launch_decode_attention(h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, 1, H, 128,
-                                        c.max_seq, pos + 1, scale, st));
-        chain[0] = TcPhase(); chain[0].mode = TC_MODE_RES; chain[0].W_tiled = w.wo_t; chain[0].N = D; chain[0].K = D;
-        chain[0].x = h->d_attn; chain[0].out = h->d_h; chain[0].res = h->d_h; chain[0].out_tagged = h->h_tag;
-        chain[1] = TcPhase(); chain[1].mode = TC_MODE_SWIGLU; chain[1].W_tiled = w.wgu_t; chain[1].N = 2 * F; chain[1].K = D;
-        chain[1].x = h->d_h; chain[1].x_tagged = h->h_tag; chain[1].norm_w = w.ln2; chain[1].out = h->d_act; chain[1].out_tagged = h->act_tag;
-        chain[2] = TcPhase(); chain[2].mode = TC_MODE_RES; chain[2].W_tiled = w.wd_t; chain[2].N = D; chain[2].K = F;
-        chain[2].x = h->d_act; chain[2].x_tagged = h->act_tag; chain[2].out = h->d_h; chain[2].res = h->d_h; chain[2].out_tagged = h->h_tag;
-        if (l + 1 < c.llm_layers) {
-          chain[3] = qkv_phase(l + 1); chain[3].x_tagged = h->h_tag;
-        } else {
-          chain[3] = TcPhase(); chain[3].mode = TC_MODE_LOGITS; chain[3].W_tiled = h->lm_head_t; chain[3].N = c.vocab;
-          chain[3].K = D; chain[3].x = h->d_h; chain[3].x_tagged = h->h_tag; chain[3].norm_w = h->norm_w; chain[3].logits = h->logits;
-        }
-        VCL_TRY(launch_gemv_tc_chain(chain, 4, cc, st));
-      }
-      if (logits_out != nullptr && logits_out != h->logits)
-        VCL_CUDA_OK(cudaMemcpyAsync(logits_out, h->logits, (size_t)c.vocab * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      if (tok_out != nullptr) VCL_TRY(launch_argmax(h->logits, tok_out, out_stride, 1, c.vocab, st));
-      return 0;
-    }
-  }
-  const bool tc_small = tc_small_batch(h, B);
+  const bool tc = tc_batch(h, B);
+  // On the ring-kernel path the embedding lookup is part of layer 0's q|k|v kernel (and with it the
+  // arg-max of the previous step); every other path gathers the rows with a kernel of its own.
+  const bool fused_embed = tc && c.llm_layers > 0;
+  VCL_REQUIRE(fused_embed || (!io.tok_from_partials && !io.partials_out), "partial arg-max hand-off needs the ring-kernel path");
+  if (!fused_embed) VCL_TRY(launch_embed_tokens(io.tok_in, io.in_stride, h->embed, h->d_h, B, D, c.vocab, st));
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlmLayerW& w = h->ll[l];
-    if (B >= 2 && B <= 16 && !tc_small) {
+    if (B >= 2 && B <= 16 && !tc) {
       GemvArgs g;
       VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln1, B, D, c.rms_eps, st));
       g.x = h->d_x; g.ldx = D; g.W = w.wqkv; g.B = B; g.N = 3 * D; g.K = D;
       VCL_TRY(launch_gemv_mma_qkv_rope(g, h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin,
-                                       H, 128, c.max_seq, pos, st));
+                                       H, 128, c.max_seq, pos, st, pd));
       VCL_TRY(launch_decode_attention(h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, B, H, 128,
-                                      c.max_seq, pos + 1, scale, st));
+                                      c.max_seq, pos + 1, scale, st, pd));
       GemvArgs go;
       go.x = h->d_attn; go.ldx = D; go.W = w.wo; go.B = B; go.N = D; go.K = D;
       VCL_TRY(launch_gemv_mma_residual(go, h->d_h, D, h->d_h, D, st));
@@ -671,10 +607,18 @@ int llm_decode_step(vcl_handle* h, const int32_t* tok_in, long long in_stride, i
     } else if (B <= 4) {
       GemvArgs g;
       g.x = h->d_h; g.ldx = D; g.W = w.wqkv; g.W_tiled = w.wqkv_t; g.B = B; g.N = 3 * D; g.K = D; g.norm_w = w.ln1; g.eps = c.rms_eps;
+      if (fused_embed && l == 0) {
+        g.x = nullptr; g.embed = h->embed; g.vocab = c.vocab; g.h_out = h->d_h;
+        if (io.tok_from_partials) {
+          g.amax_in = h->amax; g.amax_n = device_num_sms(); g.tok_out = io.tok_store; g.tok_out_stride = io.store_stride;
+        } else {
+          g.tok_in = io.tok_in; g.tok_stride = io.in_stride;
+        }
+      }
       VCL_TRY(launch_gemv_qkv_rope(g, h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin,
-                                   H, 128, c.max_seq, pos, st));
+                                   H, 128, c.max_seq, pos, st, pd));
       VCL_TRY(launch_decode_attention(h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, B, H, 128,
-                                      c.max_seq, pos + 1, scale, st));
+                                      c.max_seq, pos + 1, scale, st, pd));
       GemvArgs go;
       go.x = h->d_attn; go.ldx = D; go.W = w.wo; go.W_tiled = w.wo_t; go.B = B; go.N = D; go.K = D;
       VCL_TRY(launch_gemv_residual(go, h->d_h, D, h->d_h, D, st));
@@ -685,21 +629,42 @@ int llm_decode_step(vcl_handle* h, const int32_t* tok_in, long long in_stride, i
       gd.x = h->d_act; gd.ldx = F; gd.W = w.wd; gd.W_tiled = w.wd_t; gd.B = B; gd.N = D; gd.K = F;
       VCL_TRY(launch_gemv_residual(gd, h->d_h, D, h->d_h, D, st));
     } else {
-      // B > 4: tensor-core path, the B new rows ride in one (mostly empty) 128-row tile and the
+      // B > 16: tensor-core path, the B new rows ride in one (mostly empty) 128-row tile and the
       // N tile is narrowed so that every SM streams a slice of the weights
       VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln1, B, D, c.rms_eps, st));
       VCL_TRY(gemm(h->d_x, D, w.wqkv, D, h->d_qkv, 3 * D, nullptr, nullptr, 0, B, 3 * D, D, ACT_NONE, st));
       VCL_TRY(launch_rope_kv_prefill(h->d_qkv, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin, B,
-                                     1, H, 128, c.max_seq, pos, st));
+                                     1, H, 128, c.max_seq, pos, st, pd));
       VCL_TRY(launch_decode_attention(h->d_qkv, 3 * D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, B, H,
-                                      128, c.max_seq, pos + 1, scale, st));
+                                      128, c.max_seq, pos + 1, scale, st, pd));
       VCL_TRY(gemm(h->d_attn, D, w.wo, D, h->d_h, D, nullptr, h->d_h, D, B, D, D, ACT_NONE, st));
       VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln2, B, D, c.rms_eps, st));
       VCL_TRY(gemm(h->d_x, D, w.wgu, D, h->d_act, F, nullptr, nullptr, 0, B, 2 * F, D, ACT_SWIGLU, st));
       VCL_TRY(gemm(h->d_act, F, w.wd, F, h->d_h, D, nullptr, h->d_h, D, B, D, F, ACT_NONE, st));
     }
   }
-  VCL_TRY(lm_head_argmax(h, h->d_h, D, B, logits_out, tok_out, out_stride, st));
+  VCL_TRY(lm_head_argmax(h, h->d_h, D, B, io.logits_out, io.tok_out, io.out_stride, st, io.partials_out));
+  return 0;
+}
+
+// Steps 1 .. n_new-1 of a greedy loop over the token scratch tk [B][n_new] (tk[:, 0] is given).
+// On the ring-kernel path no arg-max / embedding kernel runs between two steps: the logits kernel
+// leaves per-CTA partials, the next step's first q|k|v kernel reduces them, records the token and
+// gathers its embedding row.
+int decode_steps(vcl_handle* h, int32_t* tk, int B, int S, int n_new, const int* pos_dev, cudaStream_t st) {
+  const bool hand_off = tc_batch(h, B) && h->cfg.llm_layers > 0;
+  for (int i = 1; i < n_new; ++i) {
+    StepIo io;
+    io.pos_dev = pos_dev;
+    if (hand_off && i > 1) {
+      io.tok_from_partials = true; io.tok_store = tk + (i - 1); io.store_stride = n_new;
+    } else {
+      io.tok_in = tk + (i - 1); io.in_stride = n_new;
+    }
+    if (hand_off && i + 1 < n_new) io.partials_out = true;
+    else { io.tok_out = tk + i; io.out_stride = n_new; }
+    VCL_TRY(llm_decode_step(h, io, B, (pos_dev ? 0 : S) + i - 1, st));
+  }
   return 0;
 }
 
@@ -707,9 +672,12 @@ int llm_decode_step(vcl_handle* h, const int32_t* tok_in, long long in_stride, i
 
 extern "C" {
 
-int vcl_clip_encode(vcl_handle* h, const void* pixels, int pixel_format, int n_frames, int n_layers,
-                    void* hidden_out, void* stream) {
+int vcl_clip_encode(vcl_handle* h, const void* pixels, int pixel_format, int n_frames, int frame_h, int frame_w,
+                    int n_layers, void* hidden_out, void* stream) {
   VCL_REQUIRE(h && pixels && hidden_out, "vcl_clip_encode: null argument");
+  VCL_REQUIRE(frame_h == h->cfg.image_size && frame_w == h->cfg.image_size,
+              "vcl_clip_encode: frames are %dx%d but the tower takes %dx%d (resize / crop them first)", frame_h,
+              frame_w, h->cfg.image_size, h->cfg.image_size);
   cudaStream_t st = as_stream(stream);
   VCL_TRY(clip_forward(h, pixels, pixel_format, n_frames, n_layers, st));
   const size_t bytes = (size_t)n_frames * (h->P + 1) * h->cfg.clip_hidden * 2;
@@ -725,9 +693,12 @@ int vcl_st_pool(const void* feats, int in_dtype, int64_t frame_stride, int64_t p
                         as_stream(stream));
 }
 
-int vcl_clip_features(vcl_handle* h, const void* pixels, int pixel_format, int n_frames, void* out,
-                      int out_dtype, void* stream) {
+int vcl_clip_features(vcl_handle* h, const void* pixels, int pixel_format, int n_frames, int frame_h, int frame_w,
+                      void* out, int out_dtype, void* stream) {
   VCL_REQUIRE(h && pixels && out, "vcl_clip_features: null argument");
+  VCL_REQUIRE(frame_h == h->cfg.image_size && frame_w == h->cfg.image_size,
+              "vcl_clip_features: frames are %dx%d but the tower takes %dx%d (resize / crop them first)", frame_h,
+              frame_w, h->cfg.image_size, h->cfg.image_size);
   cudaStream_t st = as_stream(stream);
   VCL_REQUIRE(n_frames <= h->cfg.n_temporal, "vcl_clip_features: %d frames exceed the %d temporal slots",
               n_frames, h->cfg.n_temporal);
@@ -746,6 +717,14 @@ int vcl_llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats,
                      as_stream(stream));
 }
 
+int vcl_llm_prefill_states(vcl_handle* h, const int64_t* ids, const void* video_feats,
+                           const int32_t* vid_start, int B, int S, void* states_out, float* logits_out,
+                           void* stream) {
+  VCL_REQUIRE(h != nullptr && states_out != nullptr, "vcl_llm_prefill_states: null argument");
+  return llm_prefill(h, ids, video_feats, vid_start, B, S, h->cfg.llm_layers, nullptr, logits_out, nullptr, 1,
+                     as_stream(stream), 0, states_out);
+}
+
 int vcl_llm_prefill_append(vcl_handle* h, const int64_t* ids, int B, int S, int start_pos, void* hidden_out,
                            float* logits_out, int32_t* next_tok, void* stream) {
   VCL_REQUIRE(h != nullptr && ids != nullptr, "vcl_llm_prefill_append: null argument");
@@ -759,7 +738,9 @@ int vcl_llm_decode_step(vcl_handle* h, const int32_t* tok_in, int B, int pos, fl
   VCL_REQUIRE(h && tok_in, "vcl_llm_decode_step: null argument");
   VCL_REQUIRE(h->llm_loaded, "LLM weights are not loaded");
   VCL_REQUIRE(B > 0 && B <= h->cfg.max_batch, "B=%d outside 1..%d", B, h->cfg.max_batch);
-  return llm_decode_step(h, tok_in, 1, B, pos, logits_out, tok_out, 1, as_stream(stream));
+  StepIo io;
+  io.tok_in = tok_in; io.logits_out = logits_out; io.tok_out = tok_out;
+  return llm_decode_step(h, io, B, pos, as_stream(stream));
 }
 
 int vcl_llm_decode_loop(vcl_handle* h, const int32_t* first_tok, int B, int S, int n_new,
@@ -775,16 +756,23 @@ int vcl_llm_decode_loop(vcl_handle* h, const int32_t* first_tok, int B, int S, i
     VCL_CUDA_OK(cudaMemcpy2DAsync(tk, (size_t)n_new * sizeof(int32_t), first_tok, sizeof(int32_t),
                                   sizeof(int32_t), B, cudaMemcpyDeviceToDevice, st));
   if (n_new > 1) {
+    // One graph per (B, n_new): the prompt length S reaches the kernels through h->d_pos, so a new
+    // prompt length replays the same graph. Bounded LRU cache (an entry holds thousands of nodes).
     GraphEntry* ge = nullptr;
     for (auto& g : h->graphs)
-      if (g.B == B && g.S == S && g.n_new == n_new) ge = &g;
+      if (g.B == B && g.n_new == n_new && g.S == -1) ge = &g;
     const bool can_capture = (st != nullptr) && (st != cudaStreamLegacy);
     if (ge == nullptr && can_capture) {
+      if (h->graphs.size() >= MAX_DECODE_GRAPHS) {
+        size_t victim = 0;
+        for (size_t i = 1; i < h->graphs.size(); ++i)
+          if (h->graphs[i].last_use < h->graphs[victim].last_use) victim = i;
+        cudaGraphExecDestroy(h->graphs[victim].exec);
+        h->graphs.erase(h->graphs.begin() + victim);
+      }
       const long long before = launch_count();
       VCL_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int rc = 0;
-      for (int i = 1; i < n_new && rc == 0; ++i)
-        rc = llm_decode_step(h, tk + (i - 1), n_new, B, S + i - 1, nullptr, tk + i, n_new, st);
+      const int rc = decode_steps(h, tk, B, S, n_new, h->d_pos, st);
       cudaGraph_t graph = nullptr;
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       const long long nodes = launch_count() - before;
@@ -804,15 +792,16 @@ int vcl_llm_decode_loop(vcl_handle* h, const int32_t* first_tok, int B, int S, i
         set_last_error("decode graph instantiate failed: %s", cudaGetErrorString(e));
         return -2;
       }
-      h->graphs.push_back({B, S, n_new, exec, nodes});
+      h->graphs.push_back({B, -1, n_new, exec, nodes, 0});
       ge = &h->graphs.back();
     }
     if (ge != nullptr) {
+      ge->last_use = ++h->graph_clock;
+      VCL_TRY(launch_set_int(h->d_pos, S, st));
       VCL_CUDA_OK(cudaGraphLaunch(ge->exec, st));
       count_launches(ge->kernels);
     } else {
-      for (int i = 1; i < n_new; ++i)
-        VCL_TRY(llm_decode_step(h, tk + (i - 1), n_new, B, S + i - 1, nullptr, tk + i, n_new, st));
+      VCL_TRY(decode_steps(h, tk, B, S, n_new, nullptr, st));
     }
   }
   VCL_CUDA_OK(cudaMemcpyAsync(out_tokens, tk, (size_t)B * n_new * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));

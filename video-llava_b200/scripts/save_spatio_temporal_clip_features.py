@@ -20,6 +20,8 @@ if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
 import vcl_native as vn  # noqa: E402
 
+FLUSH_EVERY = 512      # the reference writes its pending features every 512 processed videos (:129-134)
+
 
 def get_spatio_temporal_features(features, num_temporal_tokens=100):
     """[T,P,C] float16 ndarray -> [num_temporal_tokens + P, C] float16 ndarray (pooled on the GPU)."""
@@ -76,7 +78,7 @@ def main():
             counter += 1
         except Exception as e:
             print(f"Can't process {args.video_dir_path}/{name}: {e}")
-        if counter % 512 == 0:
+        if counter % FLUSH_EVERY == 0:
             flush()
     flush()
 

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libvcl.so")
 DTYPE_F16, DTYPE_BF16 = 0, 1
 PIXELS_BF16_NCHW, PIXELS_U8_NHWC = 0, 1
 PROJ_LINEAR, PROJ_MLP2X_GELU = 0, 1
+NO_VIDEO = -2 ** 31          # vid_start value of a text-only row (VCL_NO_VIDEO)
 ACT_NONE, ACT_QGELU, ACT_GELU, ACT_SWIGLU = 0, 1, 2, 3
 
 
@@ -49,12 +50,13 @@ _SIGNATURES = {
     "vcl_destroy": (None, [c_void_p]),
     "vcl_load_clip_weights": (c_int, [c_void_p, POINTER(vcl_tensor), c_int]),
     "vcl_load_llm_weights": (c_int, [c_void_p, POINTER(vcl_tensor), c_int]),
-    "vcl_clip_encode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vcl_clip_encode": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vcl_st_pool": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p,
                             c_int, c_void_p]),
-    "vcl_clip_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "vcl_clip_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "vcl_llm_prefill": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
+    "vcl_llm_prefill_states": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vcl_llm_prefill_append": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vcl_llm_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vcl_llm_generate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
@@ -239,29 +241,37 @@ class Engine:
         check(lib().vcl_load_llm_weights(self._h, arr, len(state)))
 
     # ---- vision ----
+    @staticmethod
+    def _pixels(pixels: torch.Tensor):
+        """-> (contiguous tensor, format code, frame height, frame width); the layout is told by the
+        dtype: uint8 = raw [N,H,W,3] frames, floating = normalised [N,3,H,W] pixel_values."""
+        if pixels.dim() != 4:
+            raise VclError(f"pixels must be 4-D, got shape {tuple(pixels.shape)}")
+        if pixels.dtype == torch.uint8:
+            if pixels.shape[3] != 3:
+                raise VclError(f"uint8 frames must be [N,H,W,3] (channels last), got {tuple(pixels.shape)}")
+            return pixels.contiguous(), PIXELS_U8_NHWC, pixels.shape[1], pixels.shape[2]
+        if pixels.shape[1] != 3:
+            raise VclError(f"pixel_values must be [N,3,H,W], got {tuple(pixels.shape)}")
+        return pixels.to(torch.bfloat16).contiguous(), PIXELS_BF16_NCHW, pixels.shape[2], pixels.shape[3]
+
     def clip_encode(self, pixels: torch.Tensor, n_layers: int | None = None) -> torch.Tensor:
         """pixels: [N,3,H,W] bf16 (normalised) or [N,H,W,3] uint8 -> hidden_states[n_layers] [N,1+P,C]."""
-        fmt = PIXELS_U8_NHWC if pixels.dtype == torch.uint8 else PIXELS_BF16_NCHW
-        if fmt == PIXELS_BF16_NCHW and pixels.dtype != torch.bfloat16:
-            pixels = pixels.to(torch.bfloat16)
-        pixels = pixels.contiguous()
+        pixels, fmt, fh, fw = self._pixels(pixels)
         n = pixels.shape[0]
         nl = self.cfg.clip_layers if n_layers is None else n_layers
         out = torch.empty(n, self.P + 1, self.cfg.clip_hidden, dtype=torch.bfloat16, device=pixels.device)
-        check(lib().vcl_clip_encode(self._h, ptr(pixels), fmt, n, nl, ptr(out), cur_stream()))
+        check(lib().vcl_clip_encode(self._h, ptr(pixels), fmt, n, fh, fw, nl, ptr(out), cur_stream()))
         return out
 
     def clip_features(self, pixels: torch.Tensor, out_dtype=torch.float16, out=None) -> torch.Tensor:
-        fmt = PIXELS_U8_NHWC if pixels.dtype == torch.uint8 else PIXELS_BF16_NCHW
-        if fmt == PIXELS_BF16_NCHW and pixels.dtype != torch.bfloat16:
-            pixels = pixels.to(torch.bfloat16)
-        pixels = pixels.contiguous()
+        pixels, fmt, fh, fw = self._pixels(pixels)
         if out is None:
             out = torch.empty(self.NV, self.cfg.clip_hidden, dtype=out_dtype, device=pixels.device)
         else:
             out_dtype = out.dtype
             assert out.shape == (self.NV, self.cfg.clip_hidden)
-        check(lib().vcl_clip_features(self._h, ptr(pixels), fmt, pixels.shape[0], ptr(out),
+        check(lib().vcl_clip_features(self._h, ptr(pixels), fmt, pixels.shape[0], fh, fw, ptr(out),
                                       _dtype_code(out_dtype), cur_stream()))
         return out
 
@@ -282,6 +292,21 @@ class Engine:
         check(lib().vcl_llm_prefill(self._h, ptr(ids.contiguous()), ptr(vf), ptr(vid_start.contiguous()), B, S,
                                     nl, ptr(hidden), ptr(logits), ptr(tok), cur_stream()))
         return hidden, logits, tok
+
+    def prefill_states(self, ids, video_feats, vid_start, want_logits=False):
+        """Full-depth prefill keeping every hidden state: ([L+1, B, S, D] bf16 raw layer outputs,
+        last-position logits [B, vocab] | None)."""
+        B, S = ids.shape
+        dev = ids.device
+        states = torch.empty(self.cfg.llm_layers + 1, B, S, self.cfg.llm_hidden, dtype=torch.bfloat16, device=dev)
+        logits = torch.empty(B, self.cfg.vocab, dtype=torch.float32, device=dev) if want_logits else None
+        vf = None
+        if video_feats is not None:
+            vf = video_feats.to(torch.bfloat16).contiguous()
+            assert vf.shape == (B, self.NV, self.cfg.clip_hidden), vf.shape
+        check(lib().vcl_llm_prefill_states(self._h, ptr(ids.contiguous()), ptr(vf), ptr(vid_start.contiguous()), B, S,
+                                           ptr(states), ptr(logits), cur_stream()))
+        return states, logits
 
     def prefill_append(self, ids, start_pos, want_hidden=False, want_logits=False, want_token=True):
         """Continue the cached sequences with `ids` [B, S] (text only) at positions start_pos.. ;

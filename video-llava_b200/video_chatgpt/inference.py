@@ -97,10 +97,14 @@ def video_chatgpt_infer(video_frames, question, conv_mode, model, vision_tower, 
     input_ids = torch.as_tensor(inputs.input_ids).cuda()
     stop_str = conv.sep if conv.sep_style != SeparatorStyle.TWO else conv.sep2
     stopping = KeywordsStoppingCriteria([stop_str], tokenizer, input_ids)
+    # HF generate stops at the tokenizer's EOS implicitly (generation config); the stop string alone
+    # cannot: "</s>" tokenizes to [bos, eos] and is dropped by skip_special_tokens
+    eos = getattr(tokenizer, "eos_token_id", None)
     with torch.inference_mode():
         output_ids = model.generate(input_ids, video_spatio_temporal_features=feats.unsqueeze(0),
                                     do_sample=do_sample, temperature=temperature, max_new_tokens=max_new_tokens,
-                                    stopping_criteria=[stopping])
+                                    stopping_criteria=[stopping], eos_token_id=eos if eos is not None else "config",
+                                    pad_token_id=getattr(tokenizer, "pad_token_id", None))
     n_diff = (input_ids != output_ids[:, :input_ids.shape[1]]).sum().item()
     if n_diff > 0:
         print(f"[Warning] {n_diff} output_ids are not the same as the input_ids")

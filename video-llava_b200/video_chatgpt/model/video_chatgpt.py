@@ -14,7 +14,9 @@ conventions. Differences from the reference, all documented where they occur:
   * compute dtype is bf16 (BASELINE.json); `.half()` is accepted and ignored;
   * `forward` returns logits for the LAST position only, shape [B,1,V] (the reference materialises
     [B,S,V] and every caller on this path reads [:, -1]);
-  * `hidden_states` / vision `hidden_states` are lazy: an entry is computed when indexed.
+  * the vision tower's `hidden_states` are lazy: an entry is computed when indexed (the path reads [-2]);
+    the language model's `hidden_states` are the L+1 tensors HF returns (the last one after the final
+    RMSNorm), produced by ONE prefill pass.
 """
 from __future__ import annotations
 
@@ -326,7 +328,7 @@ class VideoChatGPTLlamaForCausalLM:
         starts = []
         for row in ids:
             if (row == vc.vid_patch_token).sum() == 0:
-                starts.append(-1)                      # text-only sample
+                starts.append(vn.NO_VIDEO)             # text-only sample
                 continue
             if vc.use_vid_start_end:
                 if (row == vc.vid_start_token).sum() != (row == vc.vid_end_token).sum():
@@ -345,11 +347,11 @@ class VideoChatGPTLlamaForCausalLM:
                 s0 = int(idx[0])
                 if (idx != torch.arange(s0, s0 + n_vid)).any():
                     raise ValueError("The video patch tokens should be consecutive.")
-                starts.append(s0 - 1)                  # rows s0 .. s0+n_vid-1 are replaced
+                starts.append(s0 - 1)                  # rows s0 .. s0+n_vid-1 are replaced (-1: from row 0)
         return starts
 
     def _spans_dev(self, ids, feats, n_vid):
-        starts = self._video_spans(ids, n_vid) if feats is not None else [-1] * ids.shape[0]
+        starts = self._video_spans(ids, n_vid) if feats is not None else [vn.NO_VIDEO] * ids.shape[0]
         return torch.tensor(starts, dtype=torch.int32, device="cuda")
 
     # ---- forward / generate ----------------------------------------------------------------
@@ -372,14 +374,18 @@ class VideoChatGPTLlamaForCausalLM:
             vs = self._spans_dev(ids, feats, eng.NV)
             if feats is not None:
                 feats = feats.cuda()
-            _, logits, _ = eng.prefill(ids, feats, vs, want_logits=True, want_token=False)
-            self._pos = S
             hs = None
             if output_hidden_states:
-                L = self.config.num_hidden_layers
-                # note: unlike HF, entry L is the raw output of the last layer (pre final norm)
-                hs = _LazyStates(L + 1, lambda i: eng.prefill(ids, feats, vs, n_layers=i, want_hidden=True,
-                                                              want_token=False)[0])
+                # HF's tuple: [0] the spliced input embeddings, [i] the output of layer i, and the
+                # LAST entry after the final RMSNorm ($TF/models/llama/modeling_llama.py:411-425)
+                states, logits = eng.prefill_states(ids, feats, vs, want_logits=True)
+                L, D = self.config.num_hidden_layers, self.config.hidden_size
+                norm_w = self._state["model.norm.weight"].to(device="cuda", dtype=torch.bfloat16).contiguous()
+                last = vn.op_rmsnorm(states[L].reshape(B * S, D), norm_w, self.config.rms_norm_eps).view(B, S, D)
+                hs = tuple(states[i] for i in range(L)) + (last,)
+            else:
+                _, logits, _ = eng.prefill(ids, feats, vs, want_logits=True, want_token=False)
+            self._pos = S
         return SimpleNamespace(loss=None, logits=logits.to(torch.bfloat16)[:, None, :], past_key_values=self._pos,
                                hidden_states=hs, attentions=None)
 
@@ -396,13 +402,34 @@ class VideoChatGPTLlamaForCausalLM:
                 "attention_mask": attention_mask,
                 "video_spatio_temporal_features": kwargs.get("video_spatio_temporal_features")}
 
+    _GREEDY_CHUNK = 32      # tokens per device-side decode loop between two host-side EOS checks
+
+    def _eos_pad(self, eos_token_id, pad_token_id):
+        """HF generate's defaults: eos from the (generation) config -- LLaMA / Vicuna: 2 -- and padding
+        of finished rows with pad_token_id, which falls back to the eos id. Pass eos_token_id=None to
+        decode a fixed number of tokens (the benchmark does)."""
+        if eos_token_id == "config":
+            eos_token_id = getattr(self.config, "eos_token_id", 2)
+            if isinstance(eos_token_id, (list, tuple)):
+                eos_token_id = eos_token_id[0] if eos_token_id else None
+        if pad_token_id is None:
+            pad_token_id = getattr(self.config, "pad_token_id", None)
+        if pad_token_id is None:
+            pad_token_id = eos_token_id
+        return eos_token_id, pad_token_id
+
     @torch.no_grad()
     def generate(self, input_ids, video_spatio_temporal_features=None, do_sample=False, temperature=1.0,
-                 max_new_tokens=32, stopping_criteria=None, eos_token_id=None, **kw):
-        """Returns [B, S+n] int64 INCLUDING the prompt, like HF generate (inference.py:105-120).
-        Greedy without stopping criteria / EOS runs entirely on the device (prefill + CUDA-graph
-        decode loop); sampling (temperature) or stopping criteria fall back to one C-ABI step per
-        token with the host-side check the reference also performs every step."""
+                 max_new_tokens=32, stopping_criteria=None, eos_token_id="config", pad_token_id=None, top_k=50,
+                 **kw):
+        """Returns [B, S+n] int64 INCLUDING the prompt, like HF generate (inference.py:105-120), and
+        like HF it stops at EOS (config.eos_token_id unless eos_token_id is given; None disables it):
+        finished rows are padded, the call returns when every row has finished.
+        Greedy decoding without stopping criteria runs on the device: prefill + CUDA-graph decode
+        loops of 32 tokens with one host-side EOS check per loop (a single loop of exactly
+        max_new_tokens when EOS is disabled). Sampling (temperature, top-k 50 as HF defaults) or
+        stopping criteria take one C-ABI step per token with the host-side check the reference also
+        performs every step."""
         eng = self._ensure_engine(need_llm=True)
         ids = input_ids.cuda().to(torch.int64)
         B, S = ids.shape
@@ -413,19 +440,47 @@ class VideoChatGPTLlamaForCausalLM:
         n = min(max_new_tokens, self._max_seq - S)
         if n <= 0:
             raise ValueError(f"prompt length {S} leaves no room in max_seq {self._max_seq}")
-        stepwise = do_sample or stopping_criteria or eos_token_id is not None
-        if not stepwise:
+        eos, pad = self._eos_pad(eos_token_id, pad_token_id)
+        if do_sample or stopping_criteria:
+            _, logits, _ = eng.prefill(ids, feats, vs, want_logits=True, want_token=False)
+            self._pos = S
+            self._last_out = self._stepwise(eng, ids, logits, n, do_sample, temperature, stopping_criteria, eos, pad,
+                                            top_k)
+            return self._last_out
+        if eos is None:
             new = eng.generate(ids, feats, vs, n).to(torch.int64)
             self._pos = S + n - 1
             self._last_out = torch.cat([ids, new], dim=1)
             return self._last_out
-        _, logits, _ = eng.prefill(ids, feats, vs, want_logits=True, want_token=False)
-        self._pos = S
-        self._last_out = self._stepwise(eng, ids, logits, n, do_sample, temperature, stopping_criteria, eos_token_id)
+        # greedy with EOS: device loops of _GREEDY_CHUNK tokens, EOS looked for between them
+        c = min(n, self._GREEDY_CHUNK)
+        new = eng.generate(ids, feats, vs, c).to(torch.int64)
+        while True:
+            new, done = self._mask_finished(new, eos, pad)
+            k = new.shape[1]
+            if done or k >= n:
+                break
+            m = min(self._GREEDY_CHUNK, n - k)
+            more = eng.decode_loop(new[:, -1].to(torch.int32).contiguous(), S + k - 1, m + 1)
+            new = torch.cat([new, more[:, 1:].to(torch.int64)], dim=1)
+        self._pos = S + new.shape[1] - 1
+        self._last_out = torch.cat([ids, new], dim=1)
         return self._last_out
 
+    @staticmethod
+    def _mask_finished(new, eos, pad):
+        """Pad every row after its first EOS; when all rows have one, cut at the longest row."""
+        is_eos = new == eos
+        seen = torch.cumsum(is_eos.to(torch.int32), dim=1)
+        after = (seen - is_eos.to(torch.int32)) > 0            # strictly after the first EOS
+        new = torch.where(after, torch.full_like(new, pad), new)
+        if bool((seen[:, -1] > 0).all()):
+            first = is_eos.to(torch.int32).argmax(dim=1)
+            return new[:, : int(first.max()) + 1], True
+        return new, False
+
     def generate_continue(self, new_input_ids, do_sample=False, temperature=1.0, max_new_tokens=32,
-                          stopping_criteria=None, eos_token_id=None):
+                          stopping_criteria=None, eos_token_id="config", pad_token_id=None, top_k=50):
         """Next turn about the SAME video(s): `new_input_ids` [B, S_new] follow everything generated
         so far. Only the tokens the KV cache does not hold yet (the last generated token and the new
         text) are prefilled (vcl_llm_prefill_append); the reference re-runs the tower and the whole
@@ -440,24 +495,35 @@ class VideoChatGPTLlamaForCausalLM:
         n = min(max_new_tokens, self._max_seq - ctx.shape[1])
         if n <= 0:
             raise ValueError(f"context length {ctx.shape[1]} leaves no room in max_seq {self._max_seq}")
+        eos, pad = self._eos_pad(eos_token_id, pad_token_id)
         _, logits, _ = eng.prefill_append(tail, start, want_logits=True, want_token=False)
         self._pos = ctx.shape[1]
-        self._last_out = self._stepwise(eng, ctx, logits, n, do_sample, temperature, stopping_criteria, eos_token_id)
+        self._last_out = self._stepwise(eng, ctx, logits, n, do_sample, temperature, stopping_criteria, eos, pad, top_k)
         return self._last_out
 
-    def _stepwise(self, eng, out, logits, n, do_sample, temperature, stopping_criteria, eos_token_id):
-        for _ in range(n):
+    def _stepwise(self, eng, out, logits, n, do_sample, temperature, stopping_criteria, eos, pad, top_k=50):
+        """One token per C-ABI call. After the loop the cache holds every returned token but the last
+        (self._pos = out.shape[1] - 1), the state generate_continue starts from."""
+        unfinished = torch.ones(out.shape[0], dtype=torch.bool, device=out.device)
+        for step in range(n):
             if do_sample and temperature > 0:
-                probs = torch.softmax(logits / temperature, dim=-1)
-                nxt = torch.multinomial(probs, 1)[:, 0]
+                lg = logits / temperature
+                if top_k and top_k < lg.shape[-1]:            # HF's default warpers: temperature, then top-k 50
+                    kth = torch.topk(lg, top_k, dim=-1).values[:, -1:]
+                    lg = lg.masked_fill(lg < kth, float("-inf"))
+                nxt = torch.multinomial(torch.softmax(lg, dim=-1), 1)[:, 0]
             else:
                 nxt = logits.argmax(-1)
+            if eos is not None:
+                nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad))
             out = torch.cat([out, nxt[:, None].to(torch.int64)], dim=1)
-            if eos_token_id is not None and bool((nxt == eos_token_id).all()):
-                break
+            if eos is not None:
+                unfinished = unfinished & (nxt != eos)
+                if not bool(unfinished.any()):
+                    break
             if stopping_criteria and any(c(out, None) for c in stopping_criteria):
                 break
-            if self._pos >= self._max_seq:
+            if step + 1 == n or self._pos >= self._max_seq:
                 break
             logits, _ = eng.decode_step(nxt.to(torch.int32).contiguous(), self._pos, want_logits=True)
             self._pos += 1
