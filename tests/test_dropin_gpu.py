@@ -137,16 +137,16 @@ def test_generate_stops_at_eos_per_row_like_hf():
     m.load_state_dict(O.random_llm_state(lcfg, seed=21))
     feats = (torch.randn(2, 356, 1024, generator=torch.Generator().manual_seed(4)) * 0.5).half().cuda()
     ids = O.make_prompt_ids(lcfg, 356, seed=3, batch=2).cuda()
-    free = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=40, eos_token_id=None)
-    assert free.shape == (2, 448 + 40)
+    free = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=24, eos_token_id=None)
+    assert free.shape == (2, 448 + 24)
     new = free[:, 448:]
     eos = int(new[0, 5])                                   # row 0 finishes at step 5 (or earlier if repeated)
     first = [int((new[b] == eos).nonzero()[0]) if (new[b] == eos).any() else None for b in range(2)]
-    out = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=40, eos_token_id=eos,
+    out = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=24, eos_token_id=eos,
                      pad_token_id=0)
     got = out[:, 448:]
     if first[1] is None:                                   # row 1 never emits it: runs to the limit
-        assert got.shape[1] == 40
+        assert got.shape[1] == 24
     else:
         assert got.shape[1] == max(first) + 1
     for b in range(2):
@@ -156,7 +156,7 @@ def test_generate_stops_at_eos_per_row_like_hf():
     # the per-token path (what sampling / stopping criteria use) gives the same sequences
     class Never:
         def __call__(self, *a, **k): return False
-    out2 = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=40, eos_token_id=eos,
+    out2 = m.generate(ids, video_spatio_temporal_features=feats, do_sample=False, max_new_tokens=24, eos_token_id=eos,
                       pad_token_id=0, stopping_criteria=[Never()])
     assert torch.equal(out2, out)
     # default = config.eos_token_id (2 for LLaMA): a model that never emits 2 decodes max_new_tokens
@@ -275,6 +275,7 @@ def test_offline_extractor_main_format_resume_and_flush(tmp_path, monkeypatch):
     assert pickle.load(open(outd / "clip1.pkl", "rb")) == "sentinel" and "clip1.npy" not in seen_at_open
     # flush after every 2 processed videos: when the third processed video (clip3) is opened, the first two are on disk
     assert {"clip0.pkl", "clip2.pkl"} <= set(seen_at_open["clip3.npy"])
+    from video_chatgpt.eval.model_utils import get_seq_frames
     from video_chatgpt.train import collate_video_features, load_video_features
     csd = {k: v.cuda().bfloat16() for k, v in ck["clip_sd"].items()}
     batch = []
@@ -283,7 +284,10 @@ def test_offline_extractor_main_format_resume_and_flush(tmp_path, monkeypatch):
         assert isinstance(f, np.ndarray) and f.dtype == np.float16 and f.shape == (356, 1024)
         T = len(clips[name])
         assert (f[T:100] == 0).all() and np.abs(f[:T]).sum() > 0
-        hid = O.clip_hidden_states(csd, ck["clip_cfg"], O.preprocess_frames(clips[name]).cuda().bfloat16(), 2)[-1]
+        # load_video samples min(total, 100) frames at the reference's segment midpoints (eval/model_utils.py:55-79),
+        # which repeats / drops frames for short clips: the expectation follows the same indices
+        sampled = clips[name][get_seq_frames(T, min(T, 100))]
+        hid = O.clip_hidden_states(csd, ck["clip_cfg"], O.preprocess_frames(sampled).cuda().bfloat16(), 2)[-1]
         ref = O.st_pool_numpy(hid[:, 1:].float().cpu().numpy().astype("float16"))
         err = np.linalg.norm(f.astype(np.float32) - ref.astype(np.float32)) / np.linalg.norm(ref.astype(np.float32))
         assert err < 2e-2, (name, err)

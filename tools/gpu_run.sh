@@ -24,7 +24,7 @@ for stage in "$@"; do
   echo "=== stage $stage ($(date +%T))"
   case "$name" in
     tests)
-      if [ -z "$arg" ]; then timeout -s KILL 2400 python -m pytest tests -m gpu -x -q -s > gpurun_out/gpu_tests.log 2>&1; echo "pytest exit $?"; tail -n 5 gpurun_out/gpu_tests.log; grep "^\[parity\]\|^\[dropin\]" gpurun_out/gpu_tests.log > gpurun_out/parity_lines.txt
+      if [ -z "$arg" ]; then timeout -s KILL 2400 python -m pytest tests -m gpu -q -s > gpurun_out/gpu_tests.log 2>&1; echo "pytest exit $?"; tail -n 15 gpurun_out/gpu_tests.log; grep "^\[parity\]\|^\[dropin\]" gpurun_out/gpu_tests.log > gpurun_out/parity_lines.txt
       else timeout -s KILL 1800 python -m pytest tests -m gpu -x -q -s -k "$arg" > "gpurun_out/gpu_tests_$tag.log" 2>&1; echo "pytest exit $?"; tail -n 5 "gpurun_out/gpu_tests_$tag.log"; fi ;;
     smoke) timeout -s KILL 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 2 gpurun_out/smoke.log ;;
     bench) timeout -s KILL 1500 python bench.py $(echo "$arg" | tr ',' ' ') > "gpurun_out/bench_$tag.json" 2> "gpurun_out/bench_$tag.log"; echo "bench exit $?"; head -c 1500 "gpurun_out/bench_$tag.json"; echo ;;

@@ -512,18 +512,32 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int n_valid = FULL ? 128 : max(0, min(128, S - hf * 128));
     mbar_wait(BAR(B_S), 0);
     tc_fence_after();
-    float mx = -INFINITY;
+    // The 128 scores of this thread are read from TMEM ONCE (TMEM reads run at 64 B/clk per SM and
+    // were the largest single cost of the kernel when every score was read twice): they are rounded to
+    // bf16 right away -- the reference rounds the score tensor to bf16 before the scaling -- and kept
+    // packed in 64 registers; the row maximum is taken on the packed pairs (max commutes with rounding).
+    uint32_t st[64];
+    __nv_bfloat162 mx2 = __float2bfloat162_rn(-INFINITY);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
+    for (int c = 0; c < 8; ++c) {
+      uint32_t v[16];
       __syncwarp();
-      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_32x16(taddr + c * 16, v);
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (FULL || c * 32 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
+      for (int j = 0; j < 8; ++j) {
+        float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+        if (!FULL) {
+          if (c * 16 + 2 * j >= n_valid) a = -INFINITY;
+          if (c * 16 + 2 * j + 1 >= n_valid) b = -INFINITY;
+        }
+        const uint32_t s2 = pack_bf16x2(a, b);
+        st[c * 8 + j] = s2;
+        mx2 = __hmax2(mx2, *reinterpret_cast<const __nv_bfloat162*>(&s2));
+      }
     }
-    sm->smax[hf][r] = bf16r(mx) * SCALE;
+    const float mx = fmaxf(__low2float(mx2), __high2float(mx2));
+    sm->smax[hf][r] = mx * SCALE;
     named_bar_sync(1, T1_SM_THREADS);                         // also: all Q / K row reads are done
     const float m = fmaxf(fmaxf(sm->smax[0][r], sm->smax[1][r]), sm->s256[r]);
     const float mb = m * LOG2E;
@@ -531,20 +545,13 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      __syncwarp();
-      tmem_ld_32x32(taddr + c * 32, v);
-      tc_wait_ld();
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const uint32_t s2 = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-        float p0 = ex2_approx(fmaf(bf16lo(s2), SCALE * LOG2E, -mb));
-        float p1 = ex2_approx(fmaf(bf16hi(s2), SCALE * LOG2E, -mb));
-        if (!FULL) {
-          if (c * 32 + 2 * j >= n_valid) p0 = 0.f;
-          if (c * 32 + 2 * j + 1 >= n_valid) p1 = 0.f;
-        }
+        const uint32_t s2 = st[c * 16 + j];
+        // masked columns hold -inf: exp2(-inf) = 0, no select needed
+        const float p0 = ex2_approx(fmaf(bf16lo(s2), SCALE * LOG2E, -mb));
+        const float p1 = ex2_approx(fmaf(bf16hi(s2), SCALE * LOG2E, -mb));
         sum += p0 + p1;
         pk[j] = pack_bf16x2(p0, p1);
       }
