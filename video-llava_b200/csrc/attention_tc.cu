@@ -1,17 +1,26 @@
 // CLIP ViT self-attention on the 5th-generation tensor cores (non-causal, head_dim 64, S = P+1).
 //
-// One CTA per (frame, head). The S x S problem is tiny (257 x 257 for ViT-L/14 @224), so the whole
-// K and V of the head live in shared memory and the scores of 128 queries x 256 keys live in TMEM:
+// One CTA per (frame, head, 128-query tile), two CTAs per SM. The S x S problem is tiny (257 x 257 for
+// ViT-L/14 @224), so the whole K and V of the head live in shared memory and the scores of 128 queries x
+// 256 keys live in TMEM:
 //
-//   warp 16 (1 thread) TMA: Q, K, V tiles [256 rows x 64] of this (frame, head) straight out of the
-//                      fused qkv activation (128-B swizzle); then issues all tcgen05.mma:
-//                        S_t = Q_t . K^T      M128 x N256 x K64   -> TMEM columns [256t, 256t+256)
-//                        O_t = P_t . V        M128 x N64  x K256  -> TMEM columns [256t, 256t+64)
+//   warp 8 (1 thread)  TMA: Q tile [128 x 64], K, V tiles [256 rows x 64] of this (frame, head) straight
+//                      out of the fused qkv activation (128-B swizzle); then issues all tcgen05.mma:
+//                        S = Q . K^T      M128 x N256 x K64   -> TMEM columns [0, 256)
+//                        O = P . V        M128 x N64  x K256  -> TMEM columns [0, 64)
 //                      (V is used as an MN-major B operand, so no transpose is ever materialised)
-//   warps 0-15         softmax: thread (row, column quarter) reads its 64 score columns from TMEM
-//                      twice (max, then exp2 + sum), writes P as bf16 into a K-major swizzled smem
-//                      tile that the second MMA consumes, then normalises and stores 16 O columns
-//   warp 17            TMEM allocator; softmax + PV of query row 256 (the 257th token)
+//   warps 0-7          softmax: thread (row, column half) reads its 128 score columns from TMEM ONCE,
+//                      keeps them as packed bf16 in registers (row max on the packed pairs), then exp2,
+//                      writes P as bf16 into a K-major swizzled smem tile that the second MMA consumes,
+//                      and finally normalises and stores 32 O columns
+//   warp 9             TMEM allocator; softmax + PV of query row 256 (the 257th token)
+//
+// Measured alternatives (tools/experiments/): one CTA per (frame, head) with both tiles in 512 TMEM
+// columns (round 1: 119 us per layer against 97); a persistent CTA per SM that processes both tiles of
+// an item at once and prefetches the next item's Q / K (round 2: parity-green, 108 us against 95 -- the
+// per-CTA timeline of THIS kernel, tools/attn_trace.py, is 1.2 us set-up + 2.1 us TMA wait + 0.6 us S +
+// 0.25 us pass 1 + 1.7 us exp2 pass + 0.8 us P.V + 0.75 us epilogue = 7.4 us, and two co-resident CTAs
+// overlap each other's phases better than one CTA running its two tiles in lock-step).
 //
 // S = 257 = 2*128 + 1: the 257th KEY is folded in analytically (one extra 64-long dot product per
 // query row, added to the max / sum / output), and the 257th QUERY row is a 33k-MAC problem whose
@@ -37,27 +46,8 @@ namespace vcl {
 
 namespace {
 
-constexpr int SM_WARPS = 16;                     // softmax warps
-constexpr int SM_THREADS = SM_WARPS * 32;        // 512
-constexpr int ATC_THREADS = SM_THREADS + 64;     // + MMA/TMA warp + tail warp
 constexpr int TILE_BYTES = 256 * 128;            // 256 rows x 64 bf16
-constexpr int P_BYTES = 128 * 256 * 2;           // one P tile: 4 K-blocks of [128 x 64]
-// smem map (1024-aligned): [Q | K] 64 KB (re-used by P1), V 32 KB, P0 64 KB, small arrays
-constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = 2 * TILE_BYTES, OFF_P0 = 3 * TILE_BYTES;
-constexpr int OFF_SMALL = OFF_P0 + P_BYTES;
-constexpr int ATC_SMEM = OFF_SMALL + 12288 + 1024;
-
-struct Small {
-  unsigned long long bar[8];
-  uint32_t tmem_base, pad_[3];
-  float q256[64], k256[64], v256[64];
-  float p256[256];          // exp(s256 - rowmax) for query rows 0..255
-  float s256[256];          // scaled score of key 256 for query rows 0..255
-  float tsc[260];           // scaled scores of query 256 against keys 0..256 -> probabilities
-  float smax[2][4][128];    // [tile][column quarter][row]
-  float ssum[2][4][128];
-};
-static_assert(sizeof(Small) <= 12288, "Small");
+unsigned long long* g_attn_trace = nullptr;      // debug: set by vcl_debug_set_attn_trace (tools/attn_trace.py)
 
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {   // byte offset inside a SW128 tile
   return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
@@ -107,247 +97,6 @@ __device__ __forceinline__ float dot64(const uint8_t* tile, int row, const float
   return d;
 }
 
-// FULL: S >= 256, i.e. all 256 tensor-core key columns are valid (no masking in the inner loops)
-template <bool FULL>
-__global__ void __launch_bounds__(ATC_THREADS, 1)
-attn_vit_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const bf16* __restrict__ qkv,
-                   bf16* __restrict__ out, int S, int H, int C) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
-  uint8_t* smem = smem_raw + pad;
-  const uint32_t sbase = raw + pad;
-  Small* sm = reinterpret_cast<Small*>(smem + OFF_SMALL);
-  const uint32_t bar0 = sbase + OFF_SMALL + (uint32_t)offsetof(Small, bar);
-  auto BAR = [&](int i) { return bar0 + 8u * i; };
-  enum { B_LOAD = 0, B_S0 = 1, B_S1 = 2, B_P0 = 3, B_P1 = 4, B_O0 = 5, B_O1 = 6, B_TAIL = 7 };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x % H, n = blockIdx.x / H;
-  const long long row0 = (long long)n * S;                 // first token row of this frame
-  const int ld = 3 * C;
-  const bool key256 = S > 256;
-
-  if (warp == SM_WARPS && lane == 0) {
-    tma_prefetch_desc(&tmap_qkv);
-    mbar_init(BAR(B_LOAD), 1);
-    mbar_init(BAR(B_S0), 1); mbar_init(BAR(B_S1), 1);
-    mbar_init(BAR(B_P0), SM_THREADS); mbar_init(BAR(B_P1), SM_THREADS);
-    mbar_init(BAR(B_O0), 1); mbar_init(BAR(B_O1), 1);
-    mbar_init(BAR(B_TAIL), SM_THREADS);
-    mbar_fence_init();
-  }
-  if (warp == SM_WARPS + 1) {
-    tmem_alloc(sbase + OFF_SMALL + (uint32_t)offsetof(Small, tmem_base), 512);
-    // token 256 of q, k, v -> fp32 scalars in smem (2 values per lane)
-    const bf16* r = qkv + (row0 + 256) * ld + h * 64;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int d = lane * 2 + j;
-      sm->q256[d] = key256 ? __bfloat162float(r[d]) : 0.f;
-      sm->k256[d] = key256 ? __bfloat162float(r[C + d]) : 0.f;
-      sm->v256[d] = key256 ? __bfloat162float(r[2 * C + d]) : 0.f;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sm->tmem_base;
-  constexpr float SCALE = 0.125f;
-  constexpr float LOG2E = 1.4426950408889634f;
-
-  if (warp == SM_WARPS) {
-    if (lane == 0) {
-      // ---------------- TMA + MMA issue ----------------
-      mbar_arrive_expect_tx(BAR(B_LOAD), 3 * TILE_BYTES);
-      tma_load_2d(sbase + OFF_Q, &tmap_qkv, BAR(B_LOAD), h * 64, (int)row0);
-      tma_load_2d(sbase + OFF_K, &tmap_qkv, BAR(B_LOAD), C + h * 64, (int)row0);
-      tma_load_2d(sbase + OFF_V, &tmap_qkv, BAR(B_LOAD), 2 * C + h * 64, (int)row0);
-      mbar_wait(BAR(B_LOAD), 0);
-      tc_fence_after();
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B operand MN-major
-      const uint64_t kdesc = umma_desc_k_sw128(sbase + OFF_K);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint64_t qdesc = umma_desc_k_sw128(sbase + OFF_Q + t * 128 * 128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem + t * 256, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
-        tc_commit(BAR(B_S0 + t));
-      }
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait(BAR(B_P0 + t), 0);                 // P_t is in smem (and S_t has been consumed)
-        tc_fence_after();
-        const uint32_t pbase = sbase + (t == 0 ? OFF_P0 : OFF_Q);
-        const uint64_t vdesc = umma_desc_mn_sw128(sbase + OFF_V);
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {            // 16 keys per MMA
-          const uint64_t pdesc = umma_desc_k_sw128(pbase + (kk >> 2) * 16384) + 2u * (kk & 3);
-          tc_mma_bf16(tmem + t * 256, pdesc, vdesc + (uint64_t)((kk * 2048) >> 4), idesc_o,
-                      kk != 0 ? 1u : 0u);
-        }
-        tc_commit(BAR(B_O0 + t));
-      }
-    }
-  } else if (warp == SM_WARPS + 1) {
-    // ---------------- tail warp: query row 256 (scores come from the softmax threads) ----------------
-    if (key256) {
-      mbar_wait(BAR(B_TAIL), 0);
-      if (lane == 0) {
-        float d = 0.f;
-#pragma unroll
-        for (int c = 0; c < 64; ++c) d += sm->q256[c] * sm->k256[c];
-        sm->tsc[256] = bf16r(d) * SCALE;
-      }
-      __syncwarp();
-      float sc[9];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const int j = lane + 32 * i;
-        sc[i] = (j <= 256) ? sm->tsc[j] : -INFINITY;
-        mx = fmaxf(mx, sc[i]);
-      }
-      mx = warp_max(mx);
-      float sum = 0.f;
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const int j = lane + 32 * i;
-        const float p = (j <= 256) ? ex2_approx((sc[i] - mx) * LOG2E) : 0.f;
-        sum += p;
-        if (j <= 256) sm->tsc[j] = bf16r(p);
-      }
-      sum = warp_sum(sum);
-      __syncwarp();
-      // out[d], d = 2*lane, 2*lane+1: 8 keys per iteration keep the smem loads pipelined
-      float o0 = 0.f, o1 = 0.f;
-      const int ch = lane >> 2, wi = (lane & 3) * 4;   // 16-byte chunk and byte offset of the pair
-#pragma unroll 8
-      for (int j = 0; j < 256; ++j) {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(smem + OFF_V + sw128(j, ch) + wi);
-        const float p = sm->tsc[j];
-        o0 += p * bf16lo(v);
-        o1 += p * bf16hi(v);
-      }
-      o0 += sm->tsc[256] * sm->v256[2 * lane];
-      o1 += sm->tsc[256] * sm->v256[2 * lane + 1];
-      const float inv = 1.0f / sum;
-      *reinterpret_cast<uint32_t*>(out + (row0 + 256) * C + h * 64 + 2 * lane) =
-          pack_bf16x2(o0 * inv, o1 * inv);
-    }
-  } else {
-    // ---------------- softmax / epilogue warps ----------------
-    const int q4 = warp & 3, cq = warp >> 2;         // TMEM lane quarter, column quarter
-    const int r = q4 * 32 + lane;                    // row inside the 128-row tile
-    mbar_wait(BAR(B_LOAD), 0);
-    if (key256) {
-      // one 64-long dot product per thread: 256 x (Q row . k256) and 256 x (q256 . K row)
-      const int tix = threadIdx.x;
-      if (tix < 256) sm->s256[tix] = bf16r(dot64(smem + OFF_Q, tix, sm->k256)) * SCALE;
-      else sm->tsc[tix - 256] = bf16r(dot64(smem + OFF_K, tix - 256, sm->q256)) * SCALE;
-    } else if (threadIdx.x < 256) {
-      sm->s256[threadIdx.x] = -INFINITY;
-    }
-    mbar_arrive(BAR(B_TAIL));
-#pragma unroll 1
-    for (int t = 0; t < 2; ++t) {
-      const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + t * 256 + cq * 64;
-      const int n_valid = FULL ? 64 : max(0, min(64, S - cq * 64));
-      mbar_wait(BAR(B_S0 + t), 0);
-      tc_fence_after();
-      // pass 1: row maximum over this column quarter
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32(taddr + c * 32, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (FULL || c * 32 + j < n_valid) mx = fmaxf(mx, __uint_as_float(v[j]));
-      }
-      sm->smax[t][cq][r] = bf16r(mx) * SCALE;        // rounding and scaling are monotonic
-      named_bar_sync(1, SM_THREADS);                 // also orders the Q|K reads above before P1 writes
-      const float m = fmaxf(fmaxf(fmaxf(sm->smax[t][0][r], sm->smax[t][1][r]),
-                                  fmaxf(sm->smax[t][2][r], sm->smax[t][3][r])),
-                            sm->s256[t * 128 + r]);
-      // pass 2: p = exp(s - m) -> bf16 -> smem (K-major SW128 tile; column quarter cq = K-block cq)
-      const uint32_t pbase = (t == 0 ? OFF_P0 : OFF_Q) + cq * 16384;
-      const float mb = m * LOG2E;
-      if (cq == 0) sm->p256[t * 128 + r] = key256 ? ex2_approx(sm->s256[t * 128 + r] * LOG2E - mb) : 0.f;
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_32x32(taddr + c * 32, v);
-        tc_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t s2 = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          float p0 = ex2_approx(fmaf(bf16lo(s2), SCALE * LOG2E, -mb));
-          float p1 = ex2_approx(fmaf(bf16hi(s2), SCALE * LOG2E, -mb));
-          if (!FULL) {
-            if (c * 32 + 2 * j >= n_valid) p0 = 0.f;
-            if (c * 32 + 2 * j + 1 >= n_valid) p1 = 0.f;
-          }
-          sum += p0 + p1;
-          pk[j] = pack_bf16x2(p0, p1);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(smem + pbase + sw128(r, c * 4 + q)) =
-              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      }
-      sm->ssum[t][cq][r] = sum;
-      // generic-proxy smem writes must be visible to the tensor core (async proxy)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_fence_before();
-      mbar_arrive(BAR(B_P0 + t));
-    }
-    // ---------------- epilogue: O / sum (+ key 256), 16 columns per thread ----------------
-#pragma unroll 1
-    for (int t = 0; t < 2; ++t) {
-      mbar_wait(BAR(B_O0 + t), 0);
-      tc_fence_after();
-      uint32_t v[16];
-      __syncwarp();
-      tmem_ld_32x16(tmem + ((uint32_t)(q4 * 32) << 16) + t * 256 + cq * 16, v);
-      tc_wait_ld();
-      const int qr = t * 128 + r;
-      if (qr < S) {
-        const float p256 = sm->p256[qr];
-        const float total = sm->ssum[t][0][r] + sm->ssum[t][1][r] + sm->ssum[t][2][r] + sm->ssum[t][3][r] + p256;
-        const float inv = 1.0f / total;
-        const float pb = bf16r(p256);
-        uint32_t o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = __uint_as_float(v[2 * j]) + pb * sm->v256[cq * 16 + 2 * j];
-          const float b = __uint_as_float(v[2 * j + 1]) + pb * sm->v256[cq * 16 + 2 * j + 1];
-          o[j] = pack_bf16x2(a * inv, b * inv);
-        }
-        bf16* dst = out + (row0 + qr) * C + h * 64 + cq * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == SM_WARPS + 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------
 // Single-tile variant: one CTA per (frame, head, 128-query tile), TWO CTAs per SM (256 TMEM columns
 // and ~104 KB of shared memory each), so that one CTA's TMA / MMA / barrier latencies overlap the
@@ -377,7 +126,17 @@ static_assert(sizeof(Small1) <= 8192, "Small1");
 template <bool FULL>
 __global__ void __launch_bounds__(T1_THREADS, 2)
 attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int C) {
+                    const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int C,
+                    unsigned long long* __restrict__ trace) {
+  // optional per-CTA phase timestamps (tools/attn_trace.py); null in production
+  auto stamp = [&](int ev) {
+    if (trace != nullptr) {
+      unsigned long long t_;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+      trace[(size_t)blockIdx.x * 8 + ev] = t_;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -420,6 +179,7 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) stamp(1);
   const uint32_t tmem = sm->tmem_base;
   constexpr float SCALE = 0.125f;
   constexpr float LOG2E = 1.4426950408889634f;
@@ -500,6 +260,7 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int q4 = warp & 3, hf = warp >> 2;                  // TMEM lane quarter, column half
     const int r = q4 * 32 + lane;
     mbar_wait(BAR(B_LOAD), 0);
+    if (threadIdx.x == 0) stamp(2);
     if (key256) {
       const int tix = threadIdx.x;                            // 0..255
       if (tix < 128) sm->s256[tix] = bf16r(dot64(smem + T1_OFF_Q, tix, sm->k256)) * SCALE;
@@ -512,6 +273,7 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int n_valid = FULL ? 128 : max(0, min(128, S - hf * 128));
     mbar_wait(BAR(B_S), 0);
     tc_fence_after();
+    if (threadIdx.x == 0) stamp(3);
     // The 128 scores of this thread are read from TMEM ONCE (TMEM reads run at 64 B/clk per SM and
     // were the largest single cost of the kernel when every score was read twice): they are rounded to
     // bf16 right away -- the reference rounds the score tensor to bf16 before the scaling -- and kept
@@ -539,6 +301,7 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const float mx = fmaxf(__low2float(mx2), __high2float(mx2));
     sm->smax[hf][r] = mx * SCALE;
     named_bar_sync(1, T1_SM_THREADS);                         // also: all Q / K row reads are done
+    if (threadIdx.x == 0) stamp(4);
     const float m = fmaxf(fmaxf(sm->smax[0][r], sm->smax[1][r]), sm->s256[r]);
     const float mb = m * LOG2E;
     if (hf == 0) sm->p256[r] = key256 ? ex2_approx(sm->s256[r] * LOG2E - mb) : 0.f;
@@ -567,9 +330,11 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     mbar_arrive(BAR(B_P));
+    if (threadIdx.x == 0) stamp(5);
     // epilogue: 32 of the 64 output columns per thread
     mbar_wait(BAR(B_O), 0);
     tc_fence_after();
+    if (threadIdx.x == 0) stamp(6);
     uint32_t v[32];
     __syncwarp();
     tmem_ld_32x32(tmem + ((uint32_t)(q4 * 32) << 16) + hf * 32, v);
@@ -596,6 +361,7 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(7);
   if (warp == T1_SM_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
@@ -604,9 +370,11 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
 }  // namespace
 
+extern "C" void vcl_debug_set_attn_trace(void* dev_buffer) {
+  g_attn_trace = reinterpret_cast<unsigned long long*>(dev_buffer);
+}
+
 int init_attention_tc_kernels() {
-  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
-  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
   return 0;
@@ -617,24 +385,14 @@ int launch_attention_vit_tc(const bf16* qkv, bf16* out, int n_frames, int S, int
                             cudaStream_t stream) {
   VCL_REQUIRE(C == H * 64, "attention_tc: head_dim must be 64");
   VCL_REQUIRE(S >= 129 && S <= 257, "attention_tc: S=%d outside 129..257 (other sizes use the mma.sync kernel)", S);
-  CUtensorMap tm;
+  CUtensorMap tm, tq;
   if (make_tmap_2d(&tm, qkv, (long long)n_frames * S, 3LL * C, 3LL * C, 256) != 0) return -2;
-  static const bool two_tile = getenv("VCL_ATTN_TWO_TILE") != nullptr;   // A/B: older one-CTA-per-head kernel
-  if (!two_tile) {
-    CUtensorMap tq;
-    if (make_tmap_2d(&tq, qkv, (long long)n_frames * S, 3LL * C, 3LL * C, 128) != 0) return -2;
-    if (S >= 256)
-      attn_vit_tc1_kernel<true><<<n_frames * H * 2, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C);
-    else
-      attn_vit_tc1_kernel<false><<<n_frames * H * 2, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C);
-    VCL_CUDA_OK(cudaGetLastError());
-    count_launches(1);
-    return 0;
+  if (make_tmap_2d(&tq, qkv, (long long)n_frames * S, 3LL * C, 3LL * C, 128) != 0) return -2;
+  if (S >= 256) {
+    attn_vit_tc1_kernel<true><<<n_frames * H * 2, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, g_attn_trace);
+  } else {
+    attn_vit_tc1_kernel<false><<<n_frames * H * 2, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, g_attn_trace);
   }
-  if (S >= 256)
-    attn_vit_tc_kernel<true><<<n_frames * H, ATC_THREADS, ATC_SMEM, stream>>>(tm, qkv, out, S, H, C);
-  else
-    attn_vit_tc_kernel<false><<<n_frames * H, ATC_THREADS, ATC_SMEM, stream>>>(tm, qkv, out, S, H, C);
   VCL_CUDA_OK(cudaGetLastError());
   count_launches(1);
   return 0;

@@ -621,6 +621,8 @@ int llm_decode_step(vcl_handle* h, const StepIo& io, int B, int pos, cudaStream_
                                       c.max_seq, pos + 1, scale, st, pd));
       GemvArgs go;
       go.x = h->d_attn; go.ldx = D; go.W = w.wo; go.W_tiled = w.wo_t; go.B = B; go.N = D; go.K = D;
+      static const int o_slots = getenv("VCL_OPROJ_SLOTS") ? atoi(getenv("VCL_OPROJ_SLOTS")) : 0;   // A/B switch
+      go.ring_slots = o_slots;
       VCL_TRY(launch_gemv_residual(go, h->d_h, D, h->d_h, D, st));
       GemvArgs gg;
       gg.x = h->d_h; gg.ldx = D; gg.W = w.wgu; gg.W_tiled = w.wgu_t; gg.B = B; gg.N = 2 * F; gg.K = D; gg.norm_w = w.ln2; gg.eps = c.rms_eps;
