@@ -325,3 +325,31 @@ def test_prefill_append_matches_full_prefill(B, n_new):
         eng.prefill_append(full[:, S0:], 0)                           # a continuation needs a cache
     with pytest.raises(vn.VclError):
         eng.prefill_append(full[:, S0:], 448 + 9)                     # would run past max_seq
+
+
+@torch.no_grad()
+@pytest.mark.parametrize("NB", [5, 9, 16])
+def test_decode_wide_ring_kernel(NB):
+    """5..16 clips (width 2560) go through gemv_tcw (chunk-major walk over the slot-ordered weights, a warp
+    per row group, clip b = MMA column b): per clip it must reproduce the single-clip ring-kernel decode
+    (same weights, fp32 accumulation over the same products in another order -> bf16 noise), two steps deep."""
+    cfg = O.LlmCfg(hidden=2560, inter=6912, heads=20, layers=2)
+    sd = O.random_llm_state(cfg, seed=8)
+    ids = O.make_prompt_ids(cfg, 356, seed=6, batch=NB).to(DEV)
+    vf = (torch.randn(NB, 356, 1024, generator=torch.Generator().manual_seed(13)) * 0.5).half().float().to(DEV)
+    eng = make_engine(llm=cfg, max_batch=NB, max_seq=480)
+    sd_b = to_dev(sd)
+    eng.load_llm(sd_b)
+    vs = vid_start_of(ids, cfg)
+    _, lg, _ = eng.prefill(ids, vf, vs, want_logits=True)
+    tok = lg.argmax(-1).to(torch.int32)
+    lgb, tokb = eng.decode_step(tok, 448, want_logits=True)
+    lgb2, _ = eng.decode_step(tokb, 449, want_logits=True)
+    assert torch.equal(tokb.long(), lgb.argmax(-1))
+    for b in sorted({0, NB // 2, NB - 1}):
+        eng.prefill(ids[b:b + 1], vf[b:b + 1], vs[b:b + 1])
+        l1, t1 = eng.decode_step(tok[b:b + 1].contiguous(), 448, want_logits=True)
+        assert relerr(l1, lgb[b:b + 1]) < 1e-2, (b, relerr(l1, lgb[b:b + 1]))
+        l2, _ = eng.decode_step(tokb[b:b + 1].contiguous(), 449, want_logits=True)
+        assert relerr(l2, lgb2[b:b + 1]) < 1e-2, (b, relerr(l2, lgb2[b:b + 1]))
+    _teacher_forced_check(eng, sd_b, cfg, ids, vf, 6, f"width-2560 x2 layers B={NB} (gemv_tcw)")

@@ -30,7 +30,7 @@ ids = torch.randint(3, 32000, (B, 448), device=dev); ids[:, 64] = 32001; ids[:, 
 vs = torch.full((B,), 64, dtype=torch.int32, device=dev)
 feats = torch.empty(B, 356, 1024, dtype=torch.bfloat16, device=dev)
 for it in range(2):
-    for b in range(B):
+    for b in range(B if not os.environ.get("PROF_SKIP_VIT") else 0):
         eng.clip_features(frames, out=feats[b])
     _, _, tok = eng.prefill(ids, feats, vs)
     for i in range(2):

@@ -51,7 +51,8 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scrat
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_cluster_kernel(const bf16* __restrict__ q, long long q_ld, const bf16* __restrict__ kcache,
                            const bf16* __restrict__ vcache, bf16* __restrict__ o, long long o_ld, int H,
-                           int s_max, int kv_len, int per_cap, float scale, const int* __restrict__ pos_dev) {
+                           int s_max, int kv_len, int per_cap, float scale, const int* __restrict__ pos_dev,
+                           int o_xwin) {
   extern __shared__ float sm[];
   float* sc = sm;                       // [per_cap] scores -> probabilities of my keys
   float* red = sm + per_cap;            // [16][128] partial outputs over the 16 key groups
@@ -167,7 +168,9 @@ decode_attn_cluster_kernel(const bf16* __restrict__ q, long long q_ld, const bf1
     float v = 0.f;
 #pragma unroll
     for (uint32_t r = 0; r < DA_SPLIT; ++r) v += ld_dsmem(&outp[threadIdx.x], r);
-    o[(long long)b * o_ld + h * 128 + threadIdx.x] = __float2bfloat16_rn(v);
+    const int col = h * 128 + threadIdx.x;
+    const long long oo = o_xwin ? (long long)xwin_offset(b, col, (int)gridDim.z) : (long long)b * o_ld + col;
+    o[oo] = __float2bfloat16_rn(v);
   }
   cluster_sync_all();   // keep every CTA's shared memory alive until rank 0 has read it
 }
@@ -176,7 +179,7 @@ decode_attn_cluster_kernel(const bf16* __restrict__ q, long long q_ld, const bf1
 
 int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, const bf16* vcache,
                             bf16* o, long long o_ld, int B, int H, int head_dim, int s_max,
-                            int kv_len, float scale, cudaStream_t stream, const int* pos_dev) {
+                            int kv_len, float scale, cudaStream_t stream, const int* pos_dev, bool o_xwin) {
   VCL_REQUIRE(head_dim == 128, "decode attention: head_dim must be 128");
   VCL_REQUIRE(kv_len > 0 && kv_len <= s_max, "decode attention: kv_len %d out of range", kv_len);
   // shared memory is sized for the longest sequence when the length is only known on the device
@@ -199,7 +202,7 @@ int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, c
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_attn_cluster_kernel, q, q_ld, kcache, vcache, o, o_ld, H,
-                                 s_max, kv_len, per, scale, pos_dev));
+                                 s_max, kv_len, per, scale, pos_dev, o_xwin ? 1 : 0));
   count_launches(1);
   return 0;
 }

@@ -115,6 +115,10 @@ __global__ void __launch_bounds__(256)
 rownorm_warp_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                     const bf16* __restrict__ w, const bf16* __restrict__ b, int rows, float eps) {
   constexpr int D = CPL * 256;
+  // a following kernel launched with programmatic stream serialisation (the decode GEMVs) may become
+  // resident and prefetch its weights while the rows are normalised; it waits for this grid's completion
+  // (griddepcontrol.wait) before it reads them. No effect for ordinary successors.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * ROWS;
   if (row0 >= rows) return;
@@ -476,6 +480,54 @@ int launch_rope_kv_prefill(bf16* qkv, bf16* kcache, bf16* vcache, const bf16* co
 }
 
 __global__ void set_int_kernel(int* dst, int value) { *dst = value; }
+
+// Decode-path RMSNorm for 5..16 clips: one CTA per clip, output in the window-major layout the wide GEMV
+// streams (kernels.h: xwin). w == null: plain re-layout.
+__global__ void __launch_bounds__(256)
+xwin_norm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, const bf16* __restrict__ w, int K,
+                 float eps) {
+  __shared__ float red[8];
+  // the GEMV that follows may become resident and prefetch its weights meanwhile (it waits for this grid)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int b = blockIdx.x, B = gridDim.x, nch = K >> 3;
+  const bf16* xr = x + (long long)b * ldx;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < nch; c += 256) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / (float)K + eps);
+  for (int c = threadIdx.x; c < nch; c += 256) {
+    float v[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), v);
+    if (w != nullptr) {
+      float wv[8];
+      unpack8(*reinterpret_cast<const uint4*>(w + c * 8), wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wv[j] * bf16r(v[j] * rstd);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = v[j];
+    }
+    *reinterpret_cast<uint4*>(y + xwin_offset(b, c * 8, B)) = pack8(o);
+  }
+}
+
+int launch_xwin_norm(const bf16* x, long long ldx, bf16* y, const bf16* w, int B, int K, float eps, cudaStream_t stream) {
+  VCL_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && B > 0, "xwin_norm: K=%d / pitch must be x8", K);
+  xwin_norm_kernel<<<B, 256, 0, stream>>>(x, ldx, y, w, K, eps);
+  VCL_CUDA_OK(cudaGetLastError());
+  count_launches(1);
+  return 0;
+}
 
 int launch_set_int(int* dst, int value, cudaStream_t stream) {
   set_int_kernel<<<1, 1, 0, stream>>>(dst, value);

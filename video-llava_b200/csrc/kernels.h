@@ -100,7 +100,8 @@ int init_attention_tc_kernels();
 // single-query attention against the cache: q [B, H*hd] -> o [B, H*hd]; kv_len keys per clip
 int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, const bf16* vcache,
                             bf16* o, long long o_ld, int B, int H, int head_dim, int s_max,
-                            int kv_len, float scale, cudaStream_t stream, const int* pos_dev = nullptr);
+                            int kv_len, float scale, cudaStream_t stream, const int* pos_dev = nullptr,
+                            bool o_xwin = false);   // o_xwin: the output [B][H*hd] is written in xwin layout
 
 // ---- gemv.cu : decode-time weight streaming (M = B <= 8 rows) ------------------------------------
 // per-CTA partial arg-max of the logits kernel: the next step's q|k|v kernel reduces the grid's
@@ -181,6 +182,26 @@ int launch_gemv_tc_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16*
 int launch_gemv_tc_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
 // logits (bf16-rounded, stored fp32) [B, N]
 int launch_gemv_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
+
+// ---- gemv_tcw.cu : 5..16 clips over the slot-ordered weight copy (chunk-major K walk); the activations
+// g.x are already normalised (norm_w must be null) and stored window-major ("xwin"): element (b, k) of a
+// [B][K] activation lives at xwin_offset(b, k, B); a buffer holds xwin_elems(B, K) elements ----
+constexpr int XWIN_KC = 512, XWIN_PITCH = 544;        // 512 k per window row + 32 elements (64 B) of padding
+__host__ __device__ inline size_t xwin_offset(int b, int k, int B) {
+  return ((size_t)(k / XWIN_KC) * B + b) * XWIN_PITCH + (k % XWIN_KC);
+}
+inline size_t xwin_elems(int B, int K) { return (size_t)((K + XWIN_KC - 1) / XWIN_KC) * B * XWIN_PITCH; }
+// y (xwin layout) = x [B][ldx] rows, RMS-normalised when w != null (LlamaRMSNorm rounding order)
+int launch_xwin_norm(const bf16* x, long long ldx, bf16* y, const bf16* w, int B, int K, float eps, cudaStream_t stream);
+int init_gemv_tcw_kernels();
+bool gemv_tcw_supported(const GemvArgs& g);
+int launch_gemv_tcw_residual(const GemvArgs& g, bf16* out, long long ldo, const bf16* res, long long ldr,
+                             cudaStream_t stream);
+int launch_gemv_tcw_swiglu(const GemvArgs& g, bf16* out, long long ldo, bool out_xwin, cudaStream_t stream);
+int launch_gemv_tcw_qkv_rope(const GemvArgs& g, bf16* q_out, long long ldq, bf16* kcache, bf16* vcache,
+                             const bf16* cos_t, const bf16* sin_t, int H, int s_max, int pos, cudaStream_t stream,
+                             const int* pos_dev = nullptr);
+int launch_gemv_tcw_logits(const GemvArgs& g, float* logits, long long ldl, cudaStream_t stream);
 
 // ---- gemv_mma.cu : small-batch (2..16) decode projections on mma.sync, input already normalised ----
 int init_gemv_mma_kernels();

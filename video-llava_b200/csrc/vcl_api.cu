@@ -210,6 +210,7 @@ int vcl_create(vcl_handle** out, const vcl_config* c) {
   rc |= init_gemv_kernels();
   rc |= init_gemv_tc_kernels();
   rc |= init_gemv_mma_kernels();
+  rc |= init_gemv_tcw_kernels();
 
   const size_t C = c->clip_hidden, F = c->clip_inter;
   const size_t Mv = (size_t)c->max_frames * (h->P + 1);
@@ -238,11 +239,11 @@ int vcl_create(vcl_handle** out, const vcl_config* c) {
   rc |= dalloc(h, &h->tokens, (size_t)c->max_batch * c->max_seq);
   const size_t Bm = c->max_batch;
   rc |= dalloc(h, &h->d_h, Bm * D);
-  rc |= dalloc(h, &h->d_x, Bm * D);
+  rc |= dalloc(h, &h->d_x, xwin_elems((int)Bm, (int)D) > Bm * D ? xwin_elems((int)Bm, (int)D) : Bm * D);
   rc |= dalloc(h, &h->d_q, Bm * D);
   rc |= dalloc(h, &h->d_qkv, Bm * 3 * D);
-  rc |= dalloc(h, &h->d_attn, Bm * D);
-  rc |= dalloc(h, &h->d_act, Bm * LF);
+  rc |= dalloc(h, &h->d_attn, xwin_elems((int)Bm, (int)D) > Bm * D ? xwin_elems((int)Bm, (int)D) : Bm * D);
+  rc |= dalloc(h, &h->d_act, xwin_elems((int)Bm, (int)LF) > Bm * LF ? xwin_elems((int)Bm, (int)LF) : Bm * LF);
   rc |= dalloc(h, &h->d_pos, 4);
   rc |= dalloc(h, &h->amax, (size_t)device_num_sms() * Bm);
   if (rc == 0) rc = launch_rope_table(h->rope_cos, h->rope_sin, c->max_seq, 128, c->rope_theta, 0);
@@ -481,11 +482,16 @@ int lm_head_argmax(vcl_handle* h, const bf16* x, long long ldx, int B, float* lo
     // small batches: normalise the B rows once, then the mma.sync weight-streaming kernel
     for (int b0 = 0; b0 < B; b0 += 16) {
       const int nb = B - b0 < 16 ? B - b0 : 16;
-      VCL_TRY(launch_rmsnorm(x + (long long)b0 * ldx, ldx, h->d_x, c.llm_hidden, h->norm_w, nb, c.llm_hidden,
-                             c.rms_eps, st));
       GemvArgs g;
-      g.x = h->d_x; g.ldx = c.llm_hidden; g.W = h->lm_head; g.B = nb; g.N = c.vocab; g.K = c.llm_hidden;
-      VCL_TRY(launch_gemv_mma_logits(g, h->logits + (size_t)b0 * c.vocab, c.vocab, st));
+      g.x = h->d_x; g.ldx = c.llm_hidden; g.W = h->lm_head; g.W_tiled = h->lm_head_t; g.B = nb; g.N = c.vocab; g.K = c.llm_hidden;
+      if (gemv_tcw_supported(g)) {
+        VCL_TRY(launch_xwin_norm(x + (long long)b0 * ldx, ldx, h->d_x, h->norm_w, nb, c.llm_hidden, c.rms_eps, st));
+        VCL_TRY(launch_gemv_tcw_logits(g, h->logits + (size_t)b0 * c.vocab, c.vocab, st));
+      } else {
+        VCL_TRY(launch_rmsnorm(x + (long long)b0 * ldx, ldx, h->d_x, c.llm_hidden, h->norm_w, nb, c.llm_hidden,
+                               c.rms_eps, st));
+        VCL_TRY(launch_gemv_mma_logits(g, h->logits + (size_t)b0 * c.vocab, c.vocab, st));
+      }
     }
   } else
   for (int b0 = 0; b0 < B; b0 += 4) {
@@ -587,23 +593,37 @@ int llm_decode_step(vcl_handle* h, const StepIo& io, int B, int pos, cudaStream_
   for (int l = 0; l < c.llm_layers; ++l) {
     const LlmLayerW& w = h->ll[l];
     if (B >= 2 && B <= 16 && !tc) {
-      GemvArgs g;
-      VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln1, B, D, c.rms_eps, st));
-      g.x = h->d_x; g.ldx = D; g.W = w.wqkv; g.B = B; g.N = 3 * D; g.K = D;
-      VCL_TRY(launch_gemv_mma_qkv_rope(g, h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin,
-                                       H, 128, c.max_seq, pos, st, pd));
-      VCL_TRY(launch_decode_attention(h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, B, H, 128,
-                                      c.max_seq, pos + 1, scale, st, pd));
-      GemvArgs go;
-      go.x = h->d_attn; go.ldx = D; go.W = w.wo; go.B = B; go.N = D; go.K = D;
-      VCL_TRY(launch_gemv_mma_residual(go, h->d_h, D, h->d_h, D, st));
-      VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln2, B, D, c.rms_eps, st));
-      GemvArgs gg;
-      gg.x = h->d_x; gg.ldx = D; gg.W = w.wgu; gg.B = B; gg.N = 2 * F; gg.K = D;
-      VCL_TRY(launch_gemv_mma_swiglu(gg, h->d_act, F, st));
-      GemvArgs gd;
-      gd.x = h->d_act; gd.ldx = F; gd.W = w.wd; gd.B = B; gd.N = D; gd.K = F;
-      VCL_TRY(launch_gemv_mma_residual(gd, h->d_h, D, h->d_h, D, st));
+      GemvArgs g, go, gg, gd;
+      g.x = h->d_x; g.ldx = D; g.W = w.wqkv; g.W_tiled = w.wqkv_t; g.B = B; g.N = 3 * D; g.K = D;
+      go.x = h->d_attn; go.ldx = D; go.W = w.wo; go.W_tiled = w.wo_t; go.B = B; go.N = D; go.K = D;
+      gg.x = h->d_x; gg.ldx = D; gg.W = w.wgu; gg.W_tiled = w.wgu_t; gg.B = B; gg.N = 2 * F; gg.K = D;
+      gd.x = h->d_act; gd.ldx = F; gd.W = w.wd; gd.W_tiled = w.wd_t; gd.B = B; gd.N = D; gd.K = F;
+      if (gemv_tcw_supported(g) && gemv_tcw_supported(go) && gemv_tcw_supported(gg) && gemv_tcw_supported(gd)) {
+        // 5..16 clips: the ring kernel over the slot-ordered copy (gemv_tcw). Its inputs travel in the
+        // window-major layout (kernels.h: xwin), written by the norm, the attention kernel and its own
+        // SwiGLU epilogue; the residual stream d_h stays row-major.
+        VCL_TRY(launch_xwin_norm(h->d_h, D, h->d_x, w.ln1, B, D, c.rms_eps, st));
+        VCL_TRY(launch_gemv_tcw_qkv_rope(g, h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin, H,
+                                         c.max_seq, pos, st, pd));
+        VCL_TRY(launch_decode_attention(h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, B, H, 128,
+                                        c.max_seq, pos + 1, scale, st, pd, /*o_xwin=*/true));
+        VCL_TRY(launch_gemv_tcw_residual(go, h->d_h, D, h->d_h, D, st));
+        VCL_TRY(launch_xwin_norm(h->d_h, D, h->d_x, w.ln2, B, D, c.rms_eps, st));
+        VCL_TRY(launch_gemv_tcw_swiglu(gg, h->d_act, F, /*out_xwin=*/true, st));
+        VCL_TRY(launch_gemv_tcw_residual(gd, h->d_h, D, h->d_h, D, st));
+      } else {
+        // 2..4 clips without a slot-ordered copy, and shapes the ring kernels do not take: weights straight
+        // from global memory into MMA fragments (gemv_mma)
+        VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln1, B, D, c.rms_eps, st));
+        VCL_TRY(launch_gemv_mma_qkv_rope(g, h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin,
+                                         H, 128, c.max_seq, pos, st, pd));
+        VCL_TRY(launch_decode_attention(h->d_q, D, kc_layer(h, l), vc_layer(h, l), h->d_attn, D, B, H, 128,
+                                        c.max_seq, pos + 1, scale, st, pd));
+        VCL_TRY(launch_gemv_mma_residual(go, h->d_h, D, h->d_h, D, st));
+        VCL_TRY(launch_rmsnorm(h->d_h, D, h->d_x, D, w.ln2, B, D, c.rms_eps, st));
+        VCL_TRY(launch_gemv_mma_swiglu(gg, h->d_act, F, st));
+        VCL_TRY(launch_gemv_mma_residual(gd, h->d_h, D, h->d_h, D, st));
+      }
     } else if (B <= 4) {
       GemvArgs g;
       g.x = h->d_h; g.ldx = D; g.W = w.wqkv; g.W_tiled = w.wqkv_t; g.B = B; g.N = 3 * D; g.K = D; g.norm_w = w.ln1; g.eps = c.rms_eps;
@@ -896,27 +916,45 @@ int vcl_op_gemv(const void* x, const void* W, void* out, const void* res, const 
   if (!inited) {
     VCL_TRY(init_gemv_kernels());
     VCL_TRY(init_gemv_tc_kernels());
+    VCL_TRY(init_gemv_tcw_kernels());
     inited = true;
   }
   GemvArgs g;
   g.x = reinterpret_cast<const bf16*>(x); g.ldx = K; g.W = reinterpret_cast<const bf16*>(W);
   g.B = B; g.N = N; g.K = K; g.norm_w = reinterpret_cast<const bf16*>(norm_w); g.eps = eps;
-  // single-row case: exercise the tiled-copy kernel the decode loop uses (the copy is built here,
-  // on the fly - this entry point is a test hook, not a hot path)
-  bf16* tiled = nullptr;
-  if (B <= 4 && K % 32 == 0 && N >= 16 && getenv("VCL_GEMV_LEGACY") == nullptr) {
-    VCL_CUDA_OK(cudaMalloc(&tiled, gemv_tc_tiled_elems(N, K) * sizeof(bf16)));
-    const int rc = launch_gemv_tc_repack(g.W, tiled, N, K, false, as_stream(stream));
-    if (rc != 0) { cudaFree(tiled); return rc; }
-    g.W_tiled = tiled;
+  // exercise the slot-ordered-copy kernels the decode loop uses. The copy is built here and kept for the
+  // next call with the same matrix (this entry point is a test / micro-benchmark hook, not a hot path).
+  static const void* c_W = nullptr; static int c_N = 0, c_K = 0; static bf16* c_tiled = nullptr;
+  if (B <= 16 && K % 32 == 0 && N >= 16 && getenv("VCL_GEMV_LEGACY") == nullptr) {
+    // (the copy is only REUSED when VCL_OP_GEMV_CACHE is set -- tools/microbench.py -- because a caller may
+    // hand in a different matrix at a recycled address)
+    if (c_W != W || c_N != N || c_K != K || getenv("VCL_OP_GEMV_CACHE") == nullptr) {
+      cudaStreamSynchronize(as_stream(stream));
+      if (c_tiled != nullptr) cudaFree(c_tiled);
+      c_tiled = nullptr; c_W = nullptr;
+      VCL_CUDA_OK(cudaMalloc(&c_tiled, gemv_tc_tiled_elems(N, K) * sizeof(bf16)));
+      const int rc0 = launch_gemv_tc_repack(g.W, c_tiled, N, K, false, as_stream(stream));
+      if (rc0 != 0) { cudaFree(c_tiled); c_tiled = nullptr; return rc0; }
+      c_W = W; c_N = N; c_K = K;
+    }
+    g.W_tiled = c_tiled;
   }
-  const int rc = launch_gemv_residual(g, reinterpret_cast<bf16*>(out), N, reinterpret_cast<const bf16*>(res), N,
-                                      as_stream(stream));
-  if (tiled != nullptr) {
-    cudaStreamSynchronize(as_stream(stream));
-    cudaFree(tiled);
+  if (B >= 5) {
+    // 5..16 rows: the wide ring kernel; its input is normalised and re-laid out (xwin) by a launch of its own,
+    // as on the decode path
+    static bf16* xn = nullptr; static size_t xn_elems = 0;
+    if (xn_elems < xwin_elems(B, K)) {
+      cudaStreamSynchronize(as_stream(stream));
+      if (xn) cudaFree(xn);
+      VCL_CUDA_OK(cudaMalloc(&xn, xwin_elems(B, K) * sizeof(bf16)));
+      xn_elems = xwin_elems(B, K);
+    }
+    VCL_TRY(launch_xwin_norm(g.x, K, xn, g.norm_w, B, K, eps, as_stream(stream)));
+    g.x = xn; g.norm_w = nullptr;
+    VCL_REQUIRE(gemv_tcw_supported(g), "vcl_op_gemv: B=%d N=%d K=%d is outside the wide ring kernel's range", B, N, K);
+    return launch_gemv_tcw_residual(g, reinterpret_cast<bf16*>(out), N, reinterpret_cast<const bf16*>(res), N, as_stream(stream));
   }
-  return rc;
+  return launch_gemv_residual(g, reinterpret_cast<bf16*>(out), N, reinterpret_cast<const bf16*>(res), N, as_stream(stream));
 }
 
 }  // extern "C"
