@@ -222,3 +222,32 @@ def test_gemm_cluster_multicast(M, N, K, bn, cl, act):
     torch.cuda.synchronize()
     assert _rel(out, ref) < 3e-3, _describe(out, ref)
     assert torch.equal(out, base), _describe(out, base.float())   # same tiles, same order: bit-identical
+
+
+@pytest.mark.parametrize("M,N,K,bn,has_bias,has_res,act", [
+    (256, 256, 64, 256, False, False, vn.ACT_NONE),
+    (256, 512, 512, 256, True, False, vn.ACT_NONE),
+    (300, 1024, 1024, 256, True, True, vn.ACT_NONE),
+    (515, 4096, 1024, 256, True, False, vn.ACT_QGELU),
+    (515, 1024, 4096, 128, True, True, vn.ACT_NONE),
+    (448, 2048, 512, 128, False, False, vn.ACT_SWIGLU),
+    (448, 12288, 4096, 128, False, False, vn.ACT_NONE),
+    (25700, 3072, 1024, 256, True, False, vn.ACT_NONE),
+    (25700, 1024, 4096, 256, True, True, vn.ACT_NONE),
+])
+def test_gemm_cta_pair(M, N, K, bn, has_bias, has_res, act):
+    """cta_group::2: two CTAs drive one M = 256 MMA (each stages half of the weight tile). Same tiles and
+    the same accumulation order as the single-CTA kernel -> bit-identical results."""
+    torch.manual_seed(M + N + K + bn)
+    dev = _dev()
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev).bfloat16() if has_bias else None
+    n_out = N // 2 if act == vn.ACT_SWIGLU else N
+    res = torch.randn(M, n_out, device=dev).bfloat16() if has_res else None
+    ref, mag = _gemm_ref(a, w, bias, res, act)
+    out = vn.op_gemm(a, w, bias, res.clone() if has_res else None, act, bn, cluster=-2)
+    base = vn.op_gemm(a, w, bias, res.clone() if has_res else None, act, bn, cluster=1)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 3e-3, _describe(out, ref)
+    assert torch.equal(out, base), _describe(out, base.float())

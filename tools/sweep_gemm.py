@@ -23,9 +23,9 @@ for name, M, N, K, act in SHAPES:
     out = torch.zeros(M, N // 2 if act == vn.ACT_SWIGLU else N, device=dev, dtype=torch.bfloat16)
     res = []
     for bn in (256, 128, 64):
-        for cl in ((1, 2, 4) if bn >= 128 else (1,)):
+        for cl in ((1, 2, 4, -2) if bn >= 128 else (1,)):     # -2 = CTA pairs (cta_group::2)
             if N % bn: continue
             ms = timeit(lambda: vn.op_gemm(a, w, None, None, act, bn, out=out, cluster=cl))
             res.append((ms, bn, cl))
     best = min(res)
-    print(name, " ".join(f"bn{bn}/cl{cl}:{ms*1e3:.0f}us" for ms, bn, cl in res), f"| best bn{best[1]}/cl{best[2]} {2.0*M*N*K/best[0]/1e9:.0f} TF/s", flush=True)
+    print(name, " ".join(f"bn{bn}/{'pair' if cl == -2 else 'cl' + str(cl)}:{ms*1e3:.0f}us" for ms, bn, cl in res), f"| best bn{best[1]}/cl{best[2]} {2.0*M*N*K/best[0]/1e9:.0f} TF/s", flush=True)

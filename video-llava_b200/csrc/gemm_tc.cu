@@ -59,6 +59,130 @@ __device__ __forceinline__ float act_silu(float g) {
   return bf16r(g / (1.0f + __expf(-g)));
 }
 
+// One output tile of the epilogue, for the 32 rows x (BLOCK_N / 2) columns this warp owns: TMEM -> bias /
+// activation / residual -> bf16 -> global. warp w reads TMEM lanes 32*(w%4).. (hardware restriction) and
+// owns one half (hf) of the tile's 32-column chunks; the tcgen05.ld and the residual loads of chunk i+1
+// are issued before the math of chunk i so their latency hides behind it. wait_full() blocks until the
+// accumulator is complete, arrive_empty() hands it back to the MMA issuer once it has been read out.
+template <int BLOCK_N, int ACT, class WaitFn, class ArriveFn>
+__device__ __forceinline__ void gemm_epilogue_tile(uint32_t tmem_acc, int q4, int hf, int lane, int m_blk, int n_blk,
+                                                   bf16* C, long long ldc, const bf16* __restrict__ bias,
+                                                   const bf16* residual, long long ldr, int M, int N,
+                                                   WaitFn wait_full, ArriveFn arrive_empty) {
+  constexpr int CH = BLOCK_N / 32;
+  constexpr int PER = (CH + 1) / 2;
+  const int c_begin = hf * PER;
+  const int n_mine = (c_begin + PER <= CH) ? PER : (CH > c_begin ? CH - c_begin : 0);
+  const int row = m_blk * 128 + q4 * 32 + lane;
+  const bool row_ok = row < M;
+  const int colbase = n_blk * BLOCK_N + c_begin * 32;
+  const bf16* rrow = residual + (long long)row * ldr + colbase;
+  const bool has_res = (residual != nullptr) && row_ok;
+  uint32_t v[2][32];
+  uint4 rr[2][4];
+  if (has_res && n_mine > 0 && colbase < N) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rr[0][q] = *reinterpret_cast<const uint4*>(rrow + q * 8);
+  }
+  wait_full();
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q4 * 32) << 16) + c_begin * 32;
+  __syncwarp();
+  if (n_mine > 0) {
+    tmem_ld_32x32(taddr, v[0]);
+    tc_wait_ld();
+  }
+  if (n_mine <= 1) {
+    arrive_empty();
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    if (i < n_mine) {
+      const int cur = i & 1, nxt = cur ^ 1;
+      const int col0 = colbase + i * 32;
+      if (i + 1 < n_mine) {
+        if (has_res && col0 + 32 < N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            rr[nxt][q] = *reinterpret_cast<const uint4*>(rrow + (i + 1) * 32 + q * 8);
+        }
+        __syncwarp();
+        tmem_ld_32x32(taddr + (i + 1) * 32, v[nxt]);
+      }
+      if (row_ok && col0 < N) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[cur][j]);
+        if (bias != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 b = *reinterpret_cast<const uint4*>(bias + col0 + q * 8);
+            f[q * 8 + 0] += bf16lo(b.x); f[q * 8 + 1] += bf16hi(b.x);
+            f[q * 8 + 2] += bf16lo(b.y); f[q * 8 + 3] += bf16hi(b.y);
+            f[q * 8 + 4] += bf16lo(b.z); f[q * 8 + 5] += bf16hi(b.z);
+            f[q * 8 + 6] += bf16lo(b.w); f[q * 8 + 7] += bf16hi(b.w);
+          }
+        }
+        if constexpr (ACT == ACT_SWIGLU) {
+          // weight rows are interleaved (2j = gate_j, 2j+1 = up_j): 32 columns -> 16 outputs
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t g2 = pack_bf16x2(f[4 * j + 0], f[4 * j + 2]);   // gate pair (bf16)
+            const uint32_t u2 = pack_bf16x2(f[4 * j + 1], f[4 * j + 3]);   // up pair (bf16)
+            const float g0 = bf16lo(g2), g1 = bf16hi(g2);
+            const uint32_t s2 = pack_bf16x2(__fdividef(g0, 1.0f + __expf(-g0)),
+                                            __fdividef(g1, 1.0f + __expf(-g1)));   // silu (bf16)
+            o[j] = bf16x2_mul(s2, u2);
+          }
+          bf16* dst = C + (long long)row * ldc + (col0 >> 1);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if constexpr (ACT == ACT_QGELU) {
+              // x*sigmoid(1.702x): the three bf16 tensors of the reference are materialised
+              const uint32_t x2 = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+              const uint32_t t2 = pack_bf16x2(1.702f * bf16lo(x2), 1.702f * bf16hi(x2));
+              const uint32_t s2 = pack_bf16x2(__fdividef(1.0f, 1.0f + __expf(-bf16lo(t2))),
+                                              __fdividef(1.0f, 1.0f + __expf(-bf16hi(t2))));
+              o[j] = bf16x2_mul(x2, s2);
+            } else if constexpr (ACT == ACT_GELU) {
+              o[j] = pack_bf16x2(act_gelu_erf(f[2 * j]), act_gelu_erf(f[2 * j + 1]));
+            } else {
+              o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            }
+          }
+          if (has_res) {
+            // bf16(linear output) + residual, one more bf16 rounding (packed bf16x2 add)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              o[q * 4 + 0] = bf16x2_add(o[q * 4 + 0], rr[cur][q].x);
+              o[q * 4 + 1] = bf16x2_add(o[q * 4 + 1], rr[cur][q].y);
+              o[q * 4 + 2] = bf16x2_add(o[q * 4 + 2], rr[cur][q].z);
+              o[q * 4 + 3] = bf16x2_add(o[q * 4 + 3], rr[cur][q].w);
+            }
+          }
+          bf16* dst = C + (long long)row * ldc + col0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(dst + q * 8) =
+                make_uint4(o[q * 4 + 0], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+        }
+      }
+      if (i + 1 < n_mine) {
+        __syncwarp();
+        tc_wait_ld();
+        if (i + 2 >= n_mine) {
+          // every TMEM read of this accumulator has completed: hand it back to the MMA warp
+          arrive_empty();
+        }
+      }
+    }
+  }
+}
+
 // CL = thread-block-cluster size along M (1, 2 or 4). The CL CTAs of a cluster work on CL
 // consecutive M tiles of the SAME N tile: every CTA fetches 1/CL of the weight tile and TMA-multicasts
 // it into all CL shared memories, so a weight byte crosses L2->SM once per cluster instead of once
@@ -188,125 +312,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // math of chunk i so their latency hides behind it.
     const int q4 = warp & 3;
     const int hf = (warp - 4) >> 2;
-    constexpr int CH = BLOCK_N / 32;
-    constexpr int PER = (CH + 1) / 2;
-    const int c_begin = hf * PER;
-    const int n_mine = (c_begin + PER <= CH) ? PER : (CH > c_begin ? CH - c_begin : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
       const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
-      const int row = m_blk * Cfg::BLOCK_M + q4 * 32 + lane;
-      const bool row_ok = row < M;
-      const int colbase = n_blk * BLOCK_N + c_begin * 32;
-      const bf16* rrow = residual + (long long)row * ldr + colbase;
-      const bool has_res = (residual != nullptr) && row_ok;
-      uint32_t v[2][32];
-      uint4 rr[2][4];
-      if (has_res && n_mine > 0 && colbase < N) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rr[0][q] = *reinterpret_cast<const uint4*>(rrow + q * 8);
-      }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * BLOCK_N + c_begin * 32;
-      __syncwarp();
-      if (n_mine > 0) {
-        tmem_ld_32x32(taddr, v[0]);
-        tc_wait_ld();
-      }
-      if (n_mine <= 1) {
-        tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
-      }
-#pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        if (i < n_mine) {
-          const int cur = i & 1, nxt = cur ^ 1;
-          const int col0 = colbase + i * 32;
-          if (i + 1 < n_mine) {
-            if (has_res && col0 + 32 < N) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                rr[nxt][q] = *reinterpret_cast<const uint4*>(rrow + (i + 1) * 32 + q * 8);
-            }
-            __syncwarp();
-            tmem_ld_32x32(taddr + (i + 1) * 32, v[nxt]);
-          }
-          if (row_ok && col0 < N) {
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[cur][j]);
-            if (bias != nullptr) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 b = *reinterpret_cast<const uint4*>(bias + col0 + q * 8);
-                f[q * 8 + 0] += bf16lo(b.x); f[q * 8 + 1] += bf16hi(b.x);
-                f[q * 8 + 2] += bf16lo(b.y); f[q * 8 + 3] += bf16hi(b.y);
-                f[q * 8 + 4] += bf16lo(b.z); f[q * 8 + 5] += bf16hi(b.z);
-                f[q * 8 + 6] += bf16lo(b.w); f[q * 8 + 7] += bf16hi(b.w);
-              }
-            }
-            if constexpr (ACT == ACT_SWIGLU) {
-              // weight rows are interleaved (2j = gate_j, 2j+1 = up_j): 32 columns -> 16 outputs
-              uint32_t o[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint32_t g2 = pack_bf16x2(f[4 * j + 0], f[4 * j + 2]);   // gate pair (bf16)
-                const uint32_t u2 = pack_bf16x2(f[4 * j + 1], f[4 * j + 3]);   // up pair (bf16)
-                const float g0 = bf16lo(g2), g1 = bf16hi(g2);
-                const uint32_t s2 = pack_bf16x2(__fdividef(g0, 1.0f + __expf(-g0)),
-                                                __fdividef(g1, 1.0f + __expf(-g1)));   // silu (bf16)
-                o[j] = bf16x2_mul(s2, u2);
-              }
-              bf16* dst = C + (long long)row * ldc + (col0 >> 1);
-              *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
-            } else {
-              uint32_t o[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if constexpr (ACT == ACT_QGELU) {
-                  // x*sigmoid(1.702x): the three bf16 tensors of the reference are materialised
-                  const uint32_t x2 = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                  const uint32_t t2 = pack_bf16x2(1.702f * bf16lo(x2), 1.702f * bf16hi(x2));
-                  const uint32_t s2 = pack_bf16x2(__fdividef(1.0f, 1.0f + __expf(-bf16lo(t2))),
-                                                  __fdividef(1.0f, 1.0f + __expf(-bf16hi(t2))));
-                  o[j] = bf16x2_mul(x2, s2);
-                } else if constexpr (ACT == ACT_GELU) {
-                  o[j] = pack_bf16x2(act_gelu_erf(f[2 * j]), act_gelu_erf(f[2 * j + 1]));
-                } else {
-                  o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                }
-              }
-              if (has_res) {
-                // bf16(linear output) + residual, one more bf16 rounding (packed bf16x2 add)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  o[q * 4 + 0] = bf16x2_add(o[q * 4 + 0], rr[cur][q].x);
-                  o[q * 4 + 1] = bf16x2_add(o[q * 4 + 1], rr[cur][q].y);
-                  o[q * 4 + 2] = bf16x2_add(o[q * 4 + 2], rr[cur][q].z);
-                  o[q * 4 + 3] = bf16x2_add(o[q * 4 + 3], rr[cur][q].w);
-                }
-              }
-              bf16* dst = C + (long long)row * ldc + col0;
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(dst + q * 8) =
-                    make_uint4(o[q * 4 + 0], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
-            }
-          }
-          if (i + 1 < n_mine) {
-            __syncwarp();
-            tc_wait_ld();
-            if (i + 2 >= n_mine) {
-              // every TMEM read of this accumulator has completed: hand it back to the MMA warp
-              tc_fence_before();
-              mbar_arrive(tempty_bar(acc));
-            }
-          }
-        }
-      }
+      gemm_epilogue_tile<BLOCK_N, ACT>(
+          tmem_base + acc * BLOCK_N, q4, hf, lane, m_blk, n_blk, C, ldc, bias, residual, ldr, M, N,
+          [&]() { mbar_wait(tfull_bar(acc), acc_phase); tc_fence_after(); },
+          [&]() { tc_fence_before(); mbar_arrive(tempty_bar(acc)); });
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -322,9 +335,172 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster work on ONE 256 x BLOCK_N tile. Each
+// CTA stages its own 128 rows of A and only HALF of the weight tile (BLOCK_N / 2 rows); the leader CTA
+// issues M = 256 MMAs that read both shared memories, and each CTA finds its 128 accumulator rows in its
+// own TMEM. Against the multicast clusters above (same L2 traffic) this halves the shared-memory footprint
+// and the shared-memory reads of the weight operand per CTA: 32 KB stages, six of them.
+//   full barrier   lives in the leader, which expects the TMA bytes of BOTH CTAs; the peer's loads complete on
+//                  it too but the peer does not arrive (a remote mbarrier.arrive.release.cluster per stage
+//                  cost the peer's producer ~0.5 us and paced the whole kernel at 0.75 us per k-block).
+//                  The peer cannot run a ring turn ahead: its slot is released by the MMAs of the previous
+//                  turn, which waited for that turn's phase of this barrier
+//   empty barrier  in both CTAs, released by the leader's tcgen05.commit (multicast to the pair)
+//   tmem full      in both CTAs (multicast commit); tmem empty in the leader, 2 x 256 epilogue arrivals
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct Gemm2Cfg {
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = 128 * 64 * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;     // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static_assert(BLOCK_N == 256 || BLOCK_N == 128, "pair tiles are 256 x 256 or 256 x 128");
+};
+
+template <int BLOCK_N, int ACT>
+__global__ void __launch_bounds__(384, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, bf16* C,
+                     long long ldc, const bf16* __restrict__ bias, const bf16* residual, long long ldr, int M, int N,
+                     int K, unsigned long long* __restrict__ trace) {
+  // debug timeline (tools/gemm_pair_trace.py): [cta < 2][k-block < 128][4] globaltimer stamps; null in production
+  auto stamp = [&](int kbi, int ev) {
+    if (trace != nullptr && blockIdx.x < 2 && kbi < 128) {
+      unsigned long long t_;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+      trace[((size_t)blockIdx.x * 128 + kbi) * 4 + ev] = t_;
+    }
+  };
+  using Cfg = Gemm2Cfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw_addr + pad;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem =
+      reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                  // 0 = leader: issues the MMAs, owns the full barriers
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);            // the leader's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(empty_bar(s), 1);           // one multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 512);        // the epilogue threads of both CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_pairs = (M + 255) / 256;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_k = (K + 63) / 64;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int num_tiles = num_pairs * num_n;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int m_blk = (tile / num_n) * 2 + (int)rank, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          stamp(kb, 0);
+          mbar_wait_safe(empty_bar(stage), phase ^ 1u);
+          stamp(kb, 1);
+          const uint32_t lead_full = mapa_cluster(full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // the bytes of BOTH CTAs
+          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+          tma_load_2d_2cta(a_dst, &tmap_a, lead_full, kb * 64, m_blk * 128);
+          tma_load_2d_2cta(a_dst + Cfg::A_BYTES, &tmap_b, lead_full, kb * 64, n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader only) ------------------------------
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        mbar_wait_safe(tempty_bar(acc), acc_phase ^ 1u);     // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k; ++kb) {
+          stamp(kb, 2);
+          mbar_wait_safe(full_bar(stage), phase);
+          tc_fence_after();
+          stamp(kb, 3);
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_k_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16_2cta(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit_2cta(empty_bar(stage), 3);               // the slot is free in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit_2cta(tfull_bar(acc), 3);                   // accumulator complete -> both epilogues
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue (8 warps per CTA, own 128 rows) ------------------------------
+    const int q4 = warp & 3;
+    const int hf = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      const int m_blk = (tile / num_n) * 2 + (int)rank, n_blk = tile % num_n;
+      const uint32_t lead_tempty = mapa_cluster(tempty_bar(acc), 0);
+      gemm_epilogue_tile<BLOCK_N, ACT>(
+          tmem_base + acc * BLOCK_N, q4, hf, lane, m_blk, n_blk, C, ldc, bias, residual, ldr, M, N,
+          [&]() { mbar_wait_safe(tfull_bar(acc), acc_phase); tc_fence_after(); },
+          [&]() { tc_fence_before(); mbar_arrive_cluster(lead_tempty); });
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // nobody exits (or frees TMEM) while the peer may still read / signal it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static unsigned long long* g_gemm_trace = nullptr;     // debug: vcl_debug_set_gemm_trace
 
 static int resolve_encode() {
   if (g_encode) return 0;
@@ -369,6 +545,46 @@ int device_num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
+}
+
+template <int BLOCK_N, int ACT>
+static int launch_pair(const GemmArgs& g, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BLOCK_N>;
+  auto kern = gemm2_bf16_tn_kernel<BLOCK_N, ACT>;
+  CUtensorMap ta, tb;
+  if (make_tmap_2d(&ta, g.A, g.M, g.K, g.lda, 128) != 0) return -2;
+  if (make_tmap_2d(&tb, g.W, g.N, g.K, g.ldw, BLOCK_N / 2) != 0) return -2;
+  const int num_tiles = ((g.M + 255) / 256) * ((g.N + BLOCK_N - 1) / BLOCK_N);
+  int clusters = device_num_sms() / 2;
+  if (clusters > num_tiles) clusters = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.C, (long long)g.ldc, g.bias, g.residual, (long long)g.ldr, g.M,
+                                 g.N, g.K, g_gemm_trace));
+  count_launches(1);
+  return 0;
+}
+
+template <int BLOCK_N>
+static int launch_pair_act(const GemmArgs& g, cudaStream_t stream) {
+  switch (g.act) {
+    case ACT_NONE: return launch_pair<BLOCK_N, ACT_NONE>(g, stream);
+    case ACT_QGELU: return launch_pair<BLOCK_N, ACT_QGELU>(g, stream);
+    case ACT_GELU: return launch_pair<BLOCK_N, ACT_GELU>(g, stream);
+    case ACT_SWIGLU: return launch_pair<BLOCK_N, ACT_SWIGLU>(g, stream);
+  }
+  set_last_error("gemm: unknown activation %d", g.act);
+  return -1;
 }
 
 template <int BLOCK_N, int ACT, int CL>
@@ -445,10 +661,24 @@ static int init_bn() {
   return 0;
 }
 // Opt every instantiation into its dynamic shared memory size (done once, outside any capture).
+template <int BLOCK_N>
+static int init_pair() {
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BLOCK_N, ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BLOCK_N>::SMEM_BYTES));
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BLOCK_N, ACT_QGELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BLOCK_N>::SMEM_BYTES));
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BLOCK_N, ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BLOCK_N>::SMEM_BYTES));
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BLOCK_N, ACT_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BLOCK_N>::SMEM_BYTES));
+  return 0;
+}
+
 int init_gemm_kernels() {
   if (resolve_encode() != 0) return -2;
+  if (init_pair<256>() || init_pair<128>()) return -2;
   if (init_bn<256>() || init_bn<128>() || init_bn<64>() || init_bn<32>()) return -2;
   return 0;
+}
+
+extern "C" void vcl_debug_set_gemm_trace(void* dev_buffer) {
+  g_gemm_trace = reinterpret_cast<unsigned long long*>(dev_buffer);
 }
 
 int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
@@ -475,7 +705,10 @@ int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
     const long long mt = (g.M + 127) / 128;
     int auto_cl = 1;
     if (mt >= 16 && g.N % 256 == 0) {
-      bn = 256; auto_cl = 2;
+      // long-K tiles (ViT fc2, K = 4096): CTA pairs (cta_group::2, 256 x 256 per pair) are 2-3 % ahead of the
+      // multicast pairs; with K = 1024 the pair's longer fill / drain per tile costs more than it saves
+      // (profiles/r02_gemm_sweep.txt: q|k|v 154 vs 129 us, fc1 188 vs 166, out 57 vs 53, fc2 156 vs 160)
+      bn = 256; auto_cl = g.K >= 4096 ? -2 : 2;
     } else if (mt >= 2) {
       const int mcl = mt >= 4 ? 4 : 2;
       if (g.N % 256 == 0 && mt * (g.N / 256) >= 2 * sms) { bn = 256; auto_cl = mcl; }
@@ -492,6 +725,11 @@ int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
     if (forced_cl == 1 && mt >= 2 && mt < 16 && bn == 128 && g.N % 256 == 0 && mt * (g.N / 256) >= sms) bn = 256;
   }
   if (cl == 0) cl = 1;
+  // cluster = -2 (or VCL_GEMM_PAIR=1 for every launch with at least two row tiles): CTA pairs, cta_group::2
+  static const bool pair_all = getenv("VCL_GEMM_PAIR") != nullptr;
+  if ((cl == -2 || (pair_all && g.M > 128)) && (bn == 256 || bn == 128) && g.N % bn == 0)
+    return bn == 256 ? launch_pair_act<256>(g, stream) : launch_pair_act<128>(g, stream);
+  if (cl == -2) cl = 1;
   VCL_REQUIRE(cl == 1 || cl == 2 || cl == 4, "gemm: cluster must be 1, 2 or 4 (got %d)", cl);
   switch (bn) {
     case 256: return launch_act<256>(g, cl, stream);
