@@ -394,24 +394,16 @@ def library_sample(model, dev, clip_sd, llm_sd):
 # measured DRAM traffic of the decode loop, from the committed ncu capture
 # ---------------------------------------------------------------------------------------------
 def decode_traffic_from_ncu(model, B):
-    """Sum of dram__bytes_read + dram__bytes_write over the kernels of ONE decode step in the committed
-    `ncu --set full` summary (profiles/r02_ncu_full_decode_step.csv: one eager decode step of the 7B
-    model, 1 clip), times the steps of the loop. None when there is no capture for this configuration."""
-    path = os.path.join(ROOT, "profiles", "r02_ncu_full_decode_step.csv")
+    """Measured DRAM bytes of the decode loop: profiles/r02_decode_step_traffic.json (tools/decode_traffic.py:
+    dram__bytes_read + dram__bytes_write of every kernel of one decode step in an `ncu --set full` capture,
+    per-layer part scaled to the model depth) x the steps of the loop. None when there is no capture for
+    this configuration (7B, 1 clip)."""
+    path = os.path.join(ROOT, "profiles", "r02_decode_step_traffic.json")
     if model != "7b" or B != 1 or not os.path.exists(path):
         return None, None
     try:
-        import csv
-        rows = list(csv.reader(open(path)))
-        hdr = rows[0]
-        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        units = rows[1]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        tot = 0.0
-        for r in rows[2:]:
-            if len(r) > max(ir, iw) and r[ir]:
-                tot += float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
-        return tot * (N_NEW - 1), os.path.relpath(path, ROOT)
+        d = json.load(open(path))
+        return d["step_dram_bytes"] * (N_NEW - 1), os.path.relpath(path, ROOT) + " <- " + d["source"]
     except Exception:
         return None, None
 

@@ -158,7 +158,11 @@ int vcl_llm_decode_step(vcl_handle* h, const int32_t* tok_in, int B, int pos, fl
  * max_new_tokens=n_new) with EOS ignored (video_chatgpt/inference.py:105-112; greedy is the
  * benchmark's setting): prefill + (n_new-1) decode steps, tokens chained on
  * the device, the decode loop replayed from a CUDA graph. out_tokens is [B, n_new] int32 (new
- * tokens only; the Python shim prepends the prompt as HF does). */
+ * tokens only; the Python shim prepends the prompt as HF does).
+ * The graph is captured once per (B, n_new) on a non-default stream: the prompt length S reaches the
+ * kernels through device memory, so any S replays it; at most 6 graphs are kept (least recently used
+ * first out). With 1-4 clips no arg-max / embedding kernel runs between two steps (the logits kernel
+ * leaves per-CTA partial arg-max, the next step's first q|k|v kernel reduces them and gathers the row). */
 int vcl_llm_generate(vcl_handle* h, const int64_t* ids, const void* video_feats,
                      const int32_t* vid_start, int B, int S, int n_new, int32_t* out_tokens,
                      void* stream);
@@ -180,7 +184,8 @@ int vcl_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C,
                 const void* bias, const void* residual, int64_t ldr, int M, int N, int K, int act,
                 int block_n, void* stream);
 /* same with an explicit thread-block-cluster size along M (1, 2 or 4): the CTAs of a cluster share
- * each weight tile through TMA multicast */
+ * each weight tile through TMA multicast; cluster = -2: CTA pairs (tcgen05 cta_group::2, one M = 256 MMA
+ * per pair, each CTA stages half of the weight tile; block_n 256 or 128) */
 int vcl_op_gemm_ex(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                    const void* bias, const void* residual, int64_t ldr, int M, int N, int K, int act,
                    int block_n, int cluster, void* stream);
@@ -193,7 +198,9 @@ int vcl_op_attention(const void* q, const void* k, const void* v, void* o, int B
 /* ViT attention on the fused projection output: qkv [n_frames*S, 3*H*64] (q|k|v) -> out
  * [n_frames*S, H*64]; tcgen05 kernel, 129 <= S <= 257, non-causal, scale 64^-1/2 */
 int vcl_op_attention_vit(const void* qkv, void* out, int n_frames, int S, int H, void* stream);
-/* out[b,n] = x[b,:].W[n,:] (+res) with optional fused RMSNorm of x; B <= 4 */
+/* out[b,n] = x[b,:].W[n,:] (+res) with optional RMSNorm of x: B <= 4 the ring kernel of the single-clip
+ * decode path (fused norm), 5 <= B <= 16 the wide ring kernel (norm + window-major re-layout by a launch of
+ * its own, as on the decode path) */
 int vcl_op_gemv(const void* x, const void* W, void* out, const void* res, const void* norm_w,
                 float eps, int B, int N, int K, void* stream);
 

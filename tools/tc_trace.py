@@ -39,38 +39,22 @@ lib.vcl_debug_tc_trace_dump.argtypes = [ctypes.c_char_p]
 print("dump rc", lib.vcl_debug_tc_trace_dump(path.encode()))
 raw = np.fromfile(path, dtype=np.uint64)
 n_rec, G = int(raw[0]), int(raw[1])
-t = raw[2:].reshape(-1, G, 4, 8).astype(np.int64)
-fused = os.environ.get("VCL_DECODE_FUSED") is not None
-per_step = (L + 1) if fused else (4 * L + 1)
+t = raw[2:].reshape(-1, G, 1, 8).astype(np.int64)[:, :, 0, :]     # [launch][CTA][8 stamps]
+per_step = 4 * L + 1
 recs = t[n_rec - per_step:n_rec]
 names = {2: "qkv", 0: "res", 1: "swiglu", 3: "logits"}
-t0 = recs[0][:, 0, 0].min()
-print("fused" if fused else "unfused", "step span us", (recs[-1][:, :, 4].max() - t0) / 1e3, "launches", per_step)
-if fused:
-    # launches 1..L: [o_proj, gate/up, down, next q|k|v or logits]
-    for ph in range(4):
-        rows = []
-        for k in range(2, L):            # layers 1..L-2 (phase 3 = q|k|v)
-            r = recs[k][:, ph, :]
-            prev_end = recs[k][:, ph - 1, 4] if ph > 0 else None
-            d = dict(x_stage=(r[:, 2] - r[:, 1]).mean() / 1e3, stream=(r[:, 3] - r[:, 2]).mean() / 1e3,
-                     stream_max=(r[:, 3].max() - r[:, 2].min()) / 1e3, epi=(r[:, 4] - r[:, 3]).mean() / 1e3,
-                     barrier=((r[:, 1] - prev_end).mean() / 1e3 if ph > 0 else 0.0),
-                     barrier_last_arrival_to_release=((r[:, 1].min() - prev_end.max()) / 1e3 if ph > 0 else 0.0),
-                     phase_total=(r[:, 4].max() - (prev_end.max() if ph > 0 else r[:, 1].min())) / 1e3,
-                     producer_ahead=(r[:, 3] - r[:, 6]).mean() / 1e3)
-            rows.append(d)
-        print("phase", ph, names[int(recs[2][0, ph, 7] >> 32)], " ".join("%s=%.2f" % (kk, float(np.mean([d[kk] for d in rows]))) for kk in rows[0]))
-    lay = [(recs[k + 1][:, 0, 1].min() - recs[k][:, 0, 1].min()) / 1e3 for k in range(1, L - 1)]
-    gaps = [(recs[k + 1][:, 0, 1].min() - recs[k][:, 3, 4].max()) / 1e3 for k in range(1, L - 1)]
-    print("per-layer us", [round(x, 1) for x in lay])
-    print("fused-kernel end -> next fused kernel's dependency resolved (attention in between) us", [round(x, 1) for x in gaps])
-else:
-    for k in range(4, per_step, max(1, (per_step - 4) // 8)):
-        r = recs[k][:, 0, :]
-        print(k, names[int(r[0, 7] >> 32)], "x_stage %.2f stream %.2f/%.2f epi %.2f" % ((r[:, 2] - r[:, 1]).mean() / 1e3, (r[:, 3] - r[:, 2]).mean() / 1e3,
-              (r[:, 3].max() - r[:, 2].min()) / 1e3, (r[:, 4] - r[:, 3]).mean() / 1e3))
-    lay = [(recs[4 * (l + 1)][:, 0, 1].min() - recs[4 * l][:, 0, 1].min()) / 1e3 for l in range(L - 1)]
-    print("per-layer us", [round(x, 1) for x in lay])
-sys.stdout.flush()
-os._exit(0)
+# stamps: 0 kernel start, 1 dependency wait returned, 2 activation vector staged, 3 main loop done, 4 epilogue done,
+#         5 / 6 producer first / last copy issued, 7 = (mode << 32) | N
+print("step span us", (recs[-1][:, 4].max() - recs[0][:, 0].min()) / 1e3, "launches", per_step)
+agg = {}
+for k in range(4, per_step - 1):          # skip layer 0 and the head
+    r = recs[k]
+    mode = int(r[0, 7] >> 32); N = int(r[0, 7] & 0xffffffff)
+    key = names.get(mode, str(mode)) + f"_N{N}"
+    prev_end = recs[k - 1][:, 4].max()
+    d = dict(gap=(r[:, 1].min() - prev_end) / 1e3, x_stage=(r[:, 2] - r[:, 1]).mean() / 1e3,
+             stream=(r[:, 3] - r[:, 2]).mean() / 1e3, stream_max=(r[:, 3].max() - r[:, 2].min()) / 1e3,
+             epi=(r[:, 4] - r[:, 3]).mean() / 1e3, total=(r[:, 4].max() - prev_end) / 1e3)
+    agg.setdefault(key, []).append(d)
+for key, ds in agg.items():
+    print(key, {f: round(float(np.mean([d[f] for d in ds])), 2) for f in ds[0]})
