@@ -569,7 +569,7 @@ def run_vcl(args, rank, world, local_rank):
             del clip_sd, llm_sd
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_sample(args.model)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -650,7 +650,7 @@ def run_clip_sweep(args, rank, world, local_rank):
         "clocks": clk,
     }
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -667,7 +667,7 @@ def run_reference(args, rank, world):
         return
     s = cpu_sample(args.model)
     v = s["value"]
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": metric_name(args.config, args.model), "value": v, "unit": "videos/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": s["dtype"], "data": "synthetic",
@@ -677,7 +677,7 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
         "note": "one bounded CPU sample extrapolated to one clip of the configured workload (see cpu_baseline.sample); "
                 "the CPU arm serves one clip at a time, as the reference does",
-    }), flush=True)
+    })
 
 
 def run_library(args, rank, world, local_rank):
@@ -687,12 +687,30 @@ def run_library(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     clip_sd, llm_sd = device_weights(args.model, dev)
     lib = library_sample(args.model, dev, clip_sd, llm_sd)
-    print(json.dumps({"impl": "library", "metric": metric_name(args.config, args.model), "value": lib["eager"]["value"],
-                      "unit": "videos/s", "n_gpus": 1, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
-                      "config": workload_config(args.config, args.model, 1, 1), "library_baseline": lib}), flush=True)
+    emit({"impl": "library", "metric": metric_name(args.config, args.model), "value": lib["eager"]["value"],
+          "unit": "videos/s", "n_gpus": 1, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+          "config": workload_config(args.config, args.model, 1, 1), "library_baseline": lib})
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, written to the process's real stdout."""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line.encode())
 
 
 def main():
+    # stdout carries the JSON line and nothing else: whatever libraries print meanwhile (NCCL's version banner
+    # on some boxes, warnings) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
