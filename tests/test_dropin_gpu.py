@@ -293,3 +293,49 @@ def test_offline_extractor_main_format_resume_and_flush(tmp_path, monkeypatch):
         assert err < 2e-2, (name, err)
         batch.append({"video": f})
     assert collate_video_features(batch).shape == (3, 356, 1024)
+
+
+@torch.no_grad()
+def test_chat_py_caller_sequence(tmp_path):
+    """The call sequence of the reference's chat front end (video_chatgpt/chat.py:28-40,137-170) against the
+    mirror objects `initialize_model` returns: attribute accesses, fp16 pixel values into the tower,
+    hidden_states[-2][:, 1:], pooling, generate(do_sample=True, temperature, stopping_criteria), decode.
+    With a vanishing temperature sampling is arg-max, so the text must equal the greedy path's."""
+    from PIL import Image
+    from _checkpoint import make_tiny_checkpoint
+    from video_chatgpt.constants import DEFAULT_VID_END_TOKEN, DEFAULT_VID_START_TOKEN, DEFAULT_VIDEO_PATCH_TOKEN
+    from video_chatgpt.eval.model_utils import initialize_model
+    from video_chatgpt.inference import get_spatio_temporal_features_torch, video_chatgpt_infer
+    from video_chatgpt.model.utils import KeywordsStoppingCriteria
+    from video_chatgpt.video_conversation import SeparatorStyle, conv_templates
+    ck = make_tiny_checkpoint(tmp_path)
+    model, vision_tower, tokenizer, image_processor, video_token_len = initialize_model(ck["model_dir"], max_seq=1024)
+    frame_size = (image_processor.crop_size["height"], image_processor.crop_size["width"])
+    assert frame_size == (224, 224)
+    if model.get_model().vision_config.use_vid_start_end:
+        replace_token = DEFAULT_VID_START_TOKEN + DEFAULT_VIDEO_PATCH_TOKEN * video_token_len + DEFAULT_VID_END_TOKEN
+    else:
+        replace_token = DEFAULT_VIDEO_PATCH_TOKEN * video_token_len
+    frames = [Image.fromarray(f) for f in O.make_frames(33, 5)]
+    video_tensor = image_processor.preprocess(frames, return_tensors="pt")["pixel_values"]
+    state = conv_templates["pg-video-llava"].copy()
+    state.append_message(state.roles[0], "w20 w21 w22\n<video>")
+    state.append_message(state.roles[1], None)
+    prompt = state.get_prompt().replace("<video>", replace_token, 1)
+    input_ids = torch.as_tensor(tokenizer([prompt]).input_ids).cuda()
+    stop_str = state.sep if state.sep_style != SeparatorStyle.TWO else state.sep2
+    stopping_criteria = KeywordsStoppingCriteria([stop_str], tokenizer, input_ids)
+    video_tensor = video_tensor.half().cuda()                       # chat.py feeds fp16 pixel values
+    image_forward_outs = vision_tower(video_tensor, output_hidden_states=True)
+    frame_features = image_forward_outs.hidden_states[-2][:, 1:]
+    feats = get_spatio_temporal_features_torch(frame_features)
+    with torch.inference_mode():
+        output_ids = model.generate(input_ids, video_spatio_temporal_features=feats.unsqueeze(0), do_sample=True,
+                                    temperature=1e-4, max_new_tokens=min(8, 1536), stopping_criteria=[stopping_criteria])
+    input_token_len = input_ids.shape[1]
+    assert (input_ids != output_ids[:, :input_token_len]).sum().item() == 0
+    outputs = tokenizer.batch_decode(output_ids[:, input_token_len:], skip_special_tokens=True)[0].strip()
+    greedy = video_chatgpt_infer(frames, "w20 w21 w22", "pg-video-llava", model, vision_tower, tokenizer, image_processor,
+                                 video_token_len, do_sample=False, max_new_tokens=8)
+    print(f"[dropin] chat.py sequence -> {outputs!r}; video_chatgpt_infer (greedy) -> {greedy!r}")
+    assert outputs == greedy and len(outputs.split()) >= 1

@@ -20,11 +20,12 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace vcl {
 
 namespace {
 
-constexpr int DA_SPLIT = 4;
 constexpr int DA_THREADS = 256;
 
 // read a float at the same shared-memory offset in CTA `rank` of the cluster
@@ -48,6 +49,9 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scrat
   return r;
 }
 
+// DA_SPLIT = CTAs per (clip, head): 4 for few clips (latency: more CTAs than SMs are needed to fill the
+// machine at all), 2 or 1 when clips x heads alone oversubscribe it (throughput: fewer barriers per byte)
+template <int DA_SPLIT>
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_cluster_kernel(const bf16* __restrict__ q, long long q_ld, const bf16* __restrict__ kcache,
                            const bf16* __restrict__ vcache, bf16* __restrict__ o, long long o_ld, int H,
@@ -184,25 +188,38 @@ int launch_decode_attention(const bf16* q, long long q_ld, const bf16* kcache, c
   VCL_REQUIRE(kv_len > 0 && kv_len <= s_max, "decode attention: kv_len %d out of range", kv_len);
   // shared memory is sized for the longest sequence when the length is only known on the device
   const int kv_cap = pos_dev != nullptr ? s_max : kv_len;
-  const int per = ((kv_cap + DA_SPLIT - 1) / DA_SPLIT + 15) / 16 * 16;
+  // CTAs per head: enough CTAs to cover the SMs a few times over, no more
+  static const int forced = getenv("VCL_DA_SPLIT") ? atoi(getenv("VCL_DA_SPLIT")) : 0;      // A/B switch: 1, 2 or 4
+  const int heads = B * H;
+  // measured at 16 clips x 32 heads (config 3, decode loop of 31 steps): 4 CTAs per head 143 ms, 2: 133 ms, 1: 130 ms
+  int split = heads <= 2 * device_num_sms() ? 4 : (heads <= 3 * device_num_sms() ? 2 : 1);
+  if (forced == 1 || forced == 2 || forced == 4) split = forced;
+  const int per = ((kv_cap + split - 1) / split + 15) / 16 * 16;   // keys per CTA, multiple of 16
   const size_t smem = (size_t)(per + 16 * 128 + 128 + 2 + 8) * sizeof(float);
   VCL_REQUIRE(smem <= 48 * 1024, "decode attention: kv_len %d too long for the smem budget", kv_len);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(DA_SPLIT, H, B);
+  cfg.gridDim = dim3(split, H, B);
   cfg.blockDim = dim3(DA_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = DA_SPLIT;
+  attr[0].val.clusterDim.x = split;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_attn_cluster_kernel, q, q_ld, kcache, vcache, o, o_ld, H,
-                                 s_max, kv_len, per, scale, pos_dev, o_xwin ? 1 : 0));
+  if (split == 4)
+    VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_attn_cluster_kernel<4>, q, q_ld, kcache, vcache, o, o_ld, H, s_max, kv_len,
+                                   per, scale, pos_dev, o_xwin ? 1 : 0));
+  else if (split == 2)
+    VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_attn_cluster_kernel<2>, q, q_ld, kcache, vcache, o, o_ld, H, s_max, kv_len,
+                                   per, scale, pos_dev, o_xwin ? 1 : 0));
+  else
+    VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_attn_cluster_kernel<1>, q, q_ld, kcache, vcache, o, o_ld, H, s_max, kv_len,
+                                   per, scale, pos_dev, o_xwin ? 1 : 0));
   count_launches(1);
   return 0;
 }
