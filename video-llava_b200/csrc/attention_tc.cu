@@ -368,6 +368,276 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same tile pipeline as attn_vit_tc1_kernel with the CTA kept alive: 2 CTAs per SM walk over the
+// (frame, head, tile) work items. The per-CTA timeline of the one-shot kernel (tools/attn_trace.py) has
+// 1.2 us of set-up (TMEM allocation, barrier initialisation, descriptor prefetch), ~1.4 us of CTA relaunch
+// gap per slot and 2.1 us of TMA wait in front of 4.1 us of work; here the set-up is paid once per CTA
+// and the next tile's Q / K load is issued as soon as the P.V MMAs of the current tile have retired
+// (everything in shared memory is dead then except V, which the row-256 warp may still read: V follows
+// when the tile is finished), so it overlaps the epilogue. All barriers flip once per tile.
+// ---------------------------------------------------------------------------------------------
+template <bool FULL>
+__global__ void __launch_bounds__(T1_THREADS, 2)
+attn_vit_tc1p_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                     const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int C, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t sbase = raw + pad;
+  Small1* sm = reinterpret_cast<Small1*>(smem + T1_OFF_SMALL);
+  const uint32_t bar0 = sbase + T1_OFF_SMALL + (uint32_t)offsetof(Small1, bar);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  // B_QK: Q and K of the tile have landed; B_V: V landed; B_S: scores in TMEM; B_ROW: row 256's q/k/v vectors
+  // are in smem; B_TAIL: s256 / tsc written; B_P: P in smem; B_O: O in TMEM; B_EPI: tile finished
+  enum { B_QK = 0, B_V = 1, B_S = 2, B_ROW = 3, B_TAIL = 4, B_P = 5, B_O = 6, B_EPI = 7 };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = 3 * C;
+  const bool key256 = S > 256;
+  if (warp == T1_SM_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    mbar_init(BAR(B_QK), 1); mbar_init(BAR(B_V), 1); mbar_init(BAR(B_S), 1);
+    mbar_init(BAR(B_ROW), 32);
+    mbar_init(BAR(B_TAIL), T1_SM_THREADS);
+    mbar_init(BAR(B_P), T1_SM_THREADS);
+    mbar_init(BAR(B_O), 1);
+    mbar_init(BAR(B_EPI), T1_SM_THREADS + 32);
+    mbar_fence_init();
+  }
+  if (warp == T1_SM_WARPS + 1) tmem_alloc(sbase + T1_OFF_SMALL + (uint32_t)offsetof(Small1, tmem_base), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm->tmem_base;
+  constexpr float SCALE = 0.125f;
+  constexpr float LOG2E = 1.4426950408889634f;
+  auto p_off = [&](int kb) { return kb < 3 ? (uint32_t)(kb * 16384) : (uint32_t)T1_OFF_P3; };
+
+  if (warp == T1_SM_WARPS) {
+    // ================================ TMA + MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);
+      auto load_qk = [&](int tile) {
+        const int t = tile & 1, h = (tile >> 1) % H, n = (tile >> 1) / H;
+        const int row0 = n * S;
+        mbar_arrive_expect_tx(BAR(B_QK), 128 * 128 + TILE_BYTES);
+        tma_load_2d(sbase + T1_OFF_Q, &tmap_q, BAR(B_QK), h * 64, row0 + t * 128);
+        tma_load_2d(sbase + T1_OFF_K, &tmap_kv, BAR(B_QK), C + h * 64, row0);
+      };
+      auto load_v = [&](int tile) {
+        const int h = (tile >> 1) % H, n = (tile >> 1) / H;
+        mbar_arrive_expect_tx(BAR(B_V), TILE_BYTES);
+        tma_load_2d(sbase + T1_OFF_V, &tmap_kv, BAR(B_V), 2 * C + h * 64, n * S);
+      };
+      int tile = blockIdx.x;
+      if (tile < n_tiles) { load_qk(tile); load_v(tile); }
+      for (int i = 0; tile < n_tiles; ++i, tile += gridDim.x) {
+        const uint32_t ph = (uint32_t)(i & 1);
+        mbar_wait_safe(BAR(B_QK), ph);
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_k_sw128(sbase + T1_OFF_K);
+        const uint64_t qdesc = umma_desc_k_sw128(sbase + T1_OFF_Q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tmem, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(BAR(B_S));
+        mbar_wait_safe(BAR(B_P), ph);
+        mbar_wait_safe(BAR(B_V), ph);
+        tc_fence_after();
+        const uint64_t vdesc = umma_desc_mn_sw128(sbase + T1_OFF_V);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          const uint64_t pdesc = umma_desc_k_sw128(sbase + p_off(kk >> 2)) + 2u * (kk & 3);
+          tc_mma_bf16(tmem, pdesc, vdesc + (uint64_t)((kk * 2048) >> 4), idesc_o, kk != 0 ? 1u : 0u);
+        }
+        tc_commit(BAR(B_O));
+        const int next = tile + gridDim.x;
+        mbar_wait_safe(BAR(B_O), ph);                         // P (over Q|K) and V have been read by the MMAs
+        if (next < n_tiles) load_qk(next);                    // overlaps the epilogue of this tile
+        mbar_wait_safe(BAR(B_EPI), ph);                       // TMEM read out; the row-256 warp is done with V
+        if (next < n_tiles) load_v(next);
+      }
+    }
+  } else if (warp == T1_SM_WARPS + 1) {
+    // ================================ row 256 of the tiles with t == 1 ================================
+    int tile = blockIdx.x;
+    for (int i = 0; tile < n_tiles; ++i, tile += gridDim.x) {
+      const uint32_t ph = (uint32_t)(i & 1);
+      const int t = tile & 1, h = (tile >> 1) % H, n = (tile >> 1) / H;
+      const long long row0 = (long long)n * S;
+      const bool do_tail = key256 && t == 1;
+      const bf16* r = qkv + (row0 + 256) * ld + h * 64;
+      // the loads are in flight while the previous tile's readers of these vectors finish
+      uint32_t rq = 0, rk = 0, rv = 0;
+      if (key256) {
+        rq = *reinterpret_cast<const uint32_t*>(r + 2 * lane);
+        rk = *reinterpret_cast<const uint32_t*>(r + C + 2 * lane);
+        rv = *reinterpret_cast<const uint32_t*>(r + 2 * C + 2 * lane);
+      }
+      if (i > 0) mbar_wait_safe(BAR(B_EPI), ph ^ 1u);
+      sm->q256[2 * lane] = bf16lo(rq); sm->q256[2 * lane + 1] = bf16hi(rq);
+      sm->k256[2 * lane] = bf16lo(rk); sm->k256[2 * lane + 1] = bf16hi(rk);
+      sm->v256[2 * lane] = bf16lo(rv); sm->v256[2 * lane + 1] = bf16hi(rv);
+      mbar_arrive(BAR(B_ROW));
+      if (do_tail) {
+        mbar_wait_safe(BAR(B_TAIL), ph);
+        if (lane == 0) {
+          float d = 0.f;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) d += sm->q256[c] * sm->k256[c];
+          sm->tsc[256] = bf16r(d) * SCALE;
+        }
+        __syncwarp();
+        float sc[9];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const int j = lane + 32 * k;
+          sc[k] = (j <= 256) ? sm->tsc[j] : -INFINITY;
+          mx = fmaxf(mx, sc[k]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const int j = lane + 32 * k;
+          const float p = (j <= 256) ? ex2_approx((sc[k] - mx) * LOG2E) : 0.f;
+          sum += p;
+          if (j <= 256) sm->tsc[j] = bf16r(p);
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        mbar_wait_safe(BAR(B_V), ph);
+        float o0 = 0.f, o1 = 0.f;
+        const int ch = lane >> 2, wi = (lane & 3) * 4;
+#pragma unroll 8
+        for (int j = 0; j < 256; ++j) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(smem + T1_OFF_V + sw128(j, ch) + wi);
+          const float p = sm->tsc[j];
+          o0 += p * bf16lo(v);
+          o1 += p * bf16hi(v);
+        }
+        o0 += sm->tsc[256] * sm->v256[2 * lane];
+        o1 += sm->tsc[256] * sm->v256[2 * lane + 1];
+        const float inv = 1.0f / sum;
+        *reinterpret_cast<uint32_t*>(out + (row0 + 256) * C + h * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+      }
+      mbar_arrive(BAR(B_EPI));
+    }
+  } else {
+    // ================================ softmax warps ================================
+    const int q4 = warp & 3, hf = warp >> 2;                  // TMEM lane quarter, column half
+    const int r = q4 * 32 + lane;
+    const int tix = threadIdx.x;                              // 0..255
+    int tile = blockIdx.x;
+    for (int i = 0; tile < n_tiles; ++i, tile += gridDim.x) {
+      const uint32_t ph = (uint32_t)(i & 1);
+      const int t = tile & 1, h = (tile >> 1) % H, n = (tile >> 1) / H;
+      const long long row0 = (long long)n * S;
+      const bool do_tail = key256 && t == 1;
+      mbar_wait_safe(BAR(B_QK), ph);
+      mbar_wait_safe(BAR(B_ROW), ph);
+      if (key256) {
+        if (tix < 128) sm->s256[tix] = bf16r(dot64(smem + T1_OFF_Q, tix, sm->k256)) * SCALE;
+        if (do_tail) sm->tsc[tix] = bf16r(dot64(smem + T1_OFF_K, tix, sm->q256)) * SCALE;
+      } else if (tix < 128) {
+        sm->s256[tix] = -INFINITY;
+      }
+      mbar_arrive(BAR(B_TAIL));
+      const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + hf * 128;
+      const int n_valid = FULL ? 128 : max(0, min(128, S - hf * 128));
+      mbar_wait_safe(BAR(B_S), ph);
+      tc_fence_after();
+      uint32_t st[64];
+      __nv_bfloat162 mx2 = __float2bfloat162_rn(-INFINITY);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld_32x16(taddr + c * 16, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = __uint_as_float(v[2 * j]), b = __uint_as_float(v[2 * j + 1]);
+          if (!FULL) {
+            if (c * 16 + 2 * j >= n_valid) a = -INFINITY;
+            if (c * 16 + 2 * j + 1 >= n_valid) b = -INFINITY;
+          }
+          const uint32_t s2 = pack_bf16x2(a, b);
+          st[c * 8 + j] = s2;
+          mx2 = __hmax2(mx2, *reinterpret_cast<const __nv_bfloat162*>(&s2));
+        }
+      }
+      sm->smax[hf][r] = fmaxf(__low2float(mx2), __high2float(mx2)) * SCALE;
+      named_bar_sync(1, T1_SM_THREADS);                       // also: all Q / K row reads are done
+      const float m = fmaxf(fmaxf(sm->smax[0][r], sm->smax[1][r]), sm->s256[r]);
+      const float mb = m * LOG2E;
+      const float p256 = key256 ? ex2_approx(sm->s256[r] * LOG2E - mb) : 0.f;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t s2 = st[c * 16 + j];
+          const float p0 = ex2_approx(fmaf(bf16lo(s2), SCALE * LOG2E, -mb));
+          const float p1 = ex2_approx(fmaf(bf16hi(s2), SCALE * LOG2E, -mb));
+          sum += p0 + p1;
+          pk[j] = pack_bf16x2(p0, p1);
+        }
+        const int key0 = hf * 128 + c * 32;
+        const uint32_t pb = p_off(key0 >> 6);
+        const int ch0 = (key0 & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(smem + pb + sw128(r, ch0 + q)) =
+              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+      sm->ssum[hf][r] = sum;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(BAR(B_P));
+      mbar_wait_safe(BAR(B_O), ph);
+      tc_fence_after();
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_32x32(tmem + ((uint32_t)(q4 * 32) << 16) + hf * 32, v);
+      tc_wait_ld();
+      const int qr = t * 128 + r;
+      if (qr < S && qr < 256) {
+        const float total = sm->ssum[0][r] + sm->ssum[1][r] + p256;
+        const float inv = 1.0f / total;
+        const float pb = bf16r(p256);
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = __uint_as_float(v[2 * j]) + pb * sm->v256[hf * 32 + 2 * j];
+          const float b = __uint_as_float(v[2 * j + 1]) + pb * sm->v256[hf * 32 + 2 * j + 1];
+          o[j] = pack_bf16x2(a * inv, b * inv);
+        }
+        bf16* dst = out + (row0 + qr) * C + h * 64 + hf * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(B_EPI));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == T1_SM_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 }  // namespace
 
 extern "C" void vcl_debug_set_attn_trace(void* dev_buffer) {
@@ -377,6 +647,8 @@ extern "C" void vcl_debug_set_attn_trace(void* dev_buffer) {
 int init_attention_tc_kernels() {
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
+  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc1p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
+  VCL_CUDA_OK(cudaFuncSetAttribute(attn_vit_tc1p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T1_SMEM));
   return 0;
 }
 
@@ -388,10 +660,16 @@ int launch_attention_vit_tc(const bf16* qkv, bf16* out, int n_frames, int S, int
   CUtensorMap tm, tq;
   if (make_tmap_2d(&tm, qkv, (long long)n_frames * S, 3LL * C, 3LL * C, 256) != 0) return -2;
   if (make_tmap_2d(&tq, qkv, (long long)n_frames * S, 3LL * C, 3LL * C, 128) != 0) return -2;
-  if (S >= 256) {
-    attn_vit_tc1_kernel<true><<<n_frames * H * 2, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, g_attn_trace);
+  static const bool one_shot = getenv("VCL_ATTN_ONE_SHOT") != nullptr;   // A/B: one CTA per tile instead of persistent CTAs
+  const int n_tiles = n_frames * H * 2;
+  const int grid = n_tiles < 2 * device_num_sms() ? n_tiles : 2 * device_num_sms();
+  if (one_shot || g_attn_trace != nullptr) {
+    if (S >= 256) attn_vit_tc1_kernel<true><<<n_tiles, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, g_attn_trace);
+    else attn_vit_tc1_kernel<false><<<n_tiles, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, g_attn_trace);
+  } else if (S >= 256) {
+    attn_vit_tc1p_kernel<true><<<grid, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, n_tiles);
   } else {
-    attn_vit_tc1_kernel<false><<<n_frames * H * 2, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, g_attn_trace);
+    attn_vit_tc1p_kernel<false><<<grid, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, n_tiles);
   }
   VCL_CUDA_OK(cudaGetLastError());
   count_launches(1);

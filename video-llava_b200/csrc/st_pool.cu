@@ -12,14 +12,14 @@
 // One launch, two CTA roles, no atomics and a fixed summation order (deterministic):
 //   blockIdx <  n_temporal   temporal role: CTA reduces the P patch rows of one frame
 //   blockIdx >= n_temporal   spatial  role: CTA reduces the T frames of one patch row
-// A CTA is 8 warps and owns ONE output row x 256 channels: lane l of every warp owns 8 consecutive
-// channels (one coalesced 128-bit load per input row, 512 contiguous bytes per warp), the 8 warps deal
-// the input rows round-robin with 4 loads in flight per lane, and a fixed-order shared-memory combine
-// of the 8 partial sums finishes the mean (same summation order as a serial loop per warp: results do
-// not depend on the launch geometry). 4 x 356 = 1424 CTAs of 256 threads: eight resident per SM, i.e.
-// 128 KB of loads in flight per SM (round 1 ran 356 CTAs of 1024 threads: 2 per SM, 0.40 of the HBM
-// rate). Both roles stream the same tensor concurrently, so the second touch of a line is an L2 hit
-// rather than a second HBM read.
+// A CTA is 4 row groups x 64 lanes and owns ONE output row x 512 channels: a lane owns 8 consecutive
+// channels (one coalesced 128-bit load per input row, 1 KB contiguous per group), the 4 groups deal the
+// input rows round-robin with 8 loads in flight per lane, and a fixed-order shared-memory combine of the
+// 4 partial sums finishes the mean (deterministic). 2 x 356 = 712 CTAs of 256 threads: ALL resident at
+// once (one wave, ~5 per SM, ~150 KB of loads in flight per SM). Round 1 ran 356 CTAs of 1024 threads
+// (2 per SM, 20.4 us = 0.40 of the HBM rate); 1424 CTAs of 256 threads ran in 1.2 waves (17 us).
+// Both roles stream the same tensor concurrently, so the second touch of a line is an L2 hit rather
+// than a second HBM read.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -53,16 +53,17 @@ __device__ __forceinline__ uint32_t round_pair(float x, float y) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-constexpr int POOL_GROUPS = 8;   // warps per CTA = row groups (threadIdx.y); 32 x 8 = 256 threads
+constexpr int POOL_GROUPS = 4;   // row groups per CTA (threadIdx.y)
+constexpr int POOL_LANES = 64;   // lanes per group (threadIdx.x): 512 channels per CTA
 
 template <bool IN_BF16, bool OUT_BF16>
-__global__ void __launch_bounds__(32 * POOL_GROUPS)
+__global__ void __launch_bounds__(POOL_LANES * POOL_GROUPS)
 st_pool_kernel(const uint16_t* __restrict__ feats, long long frame_stride, long long patch_stride,
                int T, int P, int C, int n_temporal, uint16_t* __restrict__ out) {
-  constexpr int UNROLL = 4;
-  __shared__ float red[POOL_GROUPS][32 * 8];
+  constexpr int UNROLL = 8;
+  __shared__ float red[POOL_GROUPS][POOL_LANES * 8];
   const int g = threadIdx.y;
-  const int c0 = (blockIdx.y * 32 + threadIdx.x) * 8;
+  const int c0 = (blockIdx.y * POOL_LANES + threadIdx.x) * 8;
   const bool c_ok = c0 < C;
   float a[8];
 #pragma unroll
@@ -126,11 +127,11 @@ int launch_st_pool(const void* feats, int in_dtype, long long frame_stride, long
   VCL_REQUIRE(frame_stride % 8 == 0 && patch_stride % 8 == 0 && ((uintptr_t)feats % 16) == 0 &&
                   ((uintptr_t)out % 16) == 0, "st_pool: 16-byte alignment required");
   VCL_REQUIRE((in_dtype | 1) == 1 && (out_dtype | 1) == 1, "st_pool: dtype codes are 0=fp16 1=bf16");
-  dim3 grid(n_temporal + P, (C / 8 + 31) / 32);
+  dim3 grid(n_temporal + P, (C / 8 + POOL_LANES - 1) / POOL_LANES);
   const uint16_t* f = reinterpret_cast<const uint16_t*>(feats);
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
 #define VCL_POOL(IB, OB) \
-  st_pool_kernel<IB, OB><<<grid, dim3(32, POOL_GROUPS), 0, stream>>>(f, frame_stride, patch_stride, T, P, C, n_temporal, o)
+  st_pool_kernel<IB, OB><<<grid, dim3(POOL_LANES, POOL_GROUPS), 0, stream>>>(f, frame_stride, patch_stride, T, P, C, n_temporal, o)
   if (in_dtype == 1 && out_dtype == 1) VCL_POOL(true, true);
   else if (in_dtype == 1 && out_dtype == 0) VCL_POOL(true, false);
   else if (in_dtype == 0 && out_dtype == 1) VCL_POOL(false, true);
