@@ -31,6 +31,9 @@
 //               KV append, SwiGLU, residual, logits) run once at the end.
 // Ring depth: 6 slots -> 79 ms per 31 decode steps (7B), 8 -> 74 ms, 9 -> 79 ms, 13 -> 81 ms; two
 // half-SM CTAs of consecutive kernels (6 slots each) -> 77-82 ms. 8 it is.
+// An L2 look-ahead (round 2: the producer issuing cp.async.bulk.prefetch.L2 for the 4 / 8 / 16 / 32 slots of
+// its share in front of the ring, to keep HBM streaming while the ring is full during a hand-off) made the
+// decode loop slower the further it ran ahead: 76.5 / 78.2 / 83.2 / 91.4 ms against 75.8 ms without.
 //
 // Arithmetic and rounding points are those of gemv.cu (reference: transformers/models/llama/
 // modeling_llama.py:53-67 RMSNorm, :124-168 RoPE, :171-184 MLP, :325,331 residuals).
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
   float* pbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)p.x_elems * 2);
   float* result = pbuf + 2 * TC_CWARPS * 16 * 4;
   float* red = result + p.r_cap * 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4 * TC_CWARPS);
   const uint32_t ring0 = smem_u32(smem);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -186,103 +189,228 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemv_tc_kernel(const TcParams p
     // norm weights (constants) are parked in the x buffer first, every thread issues its x loads back
     // to back: the dependent latency is one L2 round trip.
     const int NB = p.nb;
-    if (ph.norm_w != nullptr) {
-      for (int b = 0; b < NB; ++b) {
+    if (NB > 1) {
+      // ---- 2-4 clips: every clip's vector is fetched at once (cp.async.cg straight into the x buffer:
+      // ONE L2 round trip for the launch instead of one per clip), then normalised in place. The norm
+      // weights (constants, the same for every clip) are parked behind the x buffer before the dependency wait.
+      bf16* nw = xs + (size_t)NB * K;                 // the plan reserves K more elements for launches with a norm
+      if (ph.norm_w != nullptr) {
 #pragma unroll
         for (int u = 0; u < XU; ++u) {
           const int c = tid + u * TC_CONSUMERS;
-          if (c < nch) *reinterpret_cast<uint4*>(xs + (size_t)b * K + c * 8) = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + c * 8));
+          if (c < nch) *reinterpret_cast<uint4*>(nw + c * 8) = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + c * 8));
         }
       }
-    }
-    float ss = 0.f;
-    if (i == 0) {
-      pdl_wait();                                    // the first activation vector comes from the previous kernel
+      pdl_wait();
       if (tid == 0) trace(i, 1);
-      for (int b = 0; b < NB; ++b) {                  // one clip after the other (one L2 round trip each)
-        bf16* xb = xs + (size_t)b * K;
-        const bf16* xg = ph.x + (long long)b * ph.ldx;
-        if (ph.embed != nullptr) {
-          // fused token-embedding gather: x = embed[token]. The token is either given (first step
-          // of a decode loop) or the arg-max of the previous step's logits, whose per-CTA partials
-          // every warp reduces for itself (same result in every warp: no barrier needed)
-          int tok;
-          if (ph.amax_in != nullptr) {
-            float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int c = lane; c < ph.amax_n; c += 32) {
-              float v; int ix;
-              asm volatile("ld.global.cg.v2.b32 {%0,%1}, [%2];" : "=f"(v), "=r"(ix) : "l"(ph.amax_in + (size_t)c * NB + b) : "memory");
-              if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+      const bf16* xg[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) xg[b] = ph.x + (long long)(b < NB ? b : 0) * ph.ldx;
+      if (ph.embed != nullptr) {
+        int tok[4] = {0, 0, 0, 0};
+        if (ph.amax_in != nullptr) {
+          // arg-max of the previous step's logits from the per-CTA partials, all clips in flight together
+          float bv[4]; int bi[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) { bv[b] = -INFINITY; bi[b] = 0x7fffffff; }
+          for (int c = lane; c < ph.amax_n; c += 32) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              if (b < NB) {
+                float v; int ix;
+                asm volatile("ld.global.cg.v2.b32 {%0,%1}, [%2];" : "=f"(v), "=r"(ix) : "l"(ph.amax_in + (size_t)c * NB + b) : "memory");
+                if (v > bv[b] || (v == bv[b] && ix < bi[b])) { bv[b] = v; bi[b] = ix; }
+              }
             }
+          }
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-              if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+              const float ov = __shfl_xor_sync(0xffffffffu, bv[b], o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi[b], o);
+              if (ov > bv[b] || (ov == bv[b] && oi < bi[b])) { bv[b] = ov; bi[b] = oi; }
             }
-            tok = bi;
-            if (blockIdx.x == 0 && tid == 0 && ph.tok_out != nullptr) ph.tok_out[(long long)b * ph.tok_out_stride] = tok;
-          } else {
-            asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(tok) : "l"(ph.tok_in + (long long)b * ph.tok_stride) : "memory");
-          }
-          tok = tok < 0 ? 0 : (tok >= ph.vocab ? ph.vocab - 1 : tok);
-          xg = ph.embed + (long long)tok * K;
-        }
-        uint4 xv[XU];
-#pragma unroll
-        for (int u = 0; u < XU; ++u) {
-          const int c = tid + u * TC_CONSUMERS;
-          xv[u] = (c < nch) ? ld_cg_v4(xg + c * 8) : make_uint4(0, 0, 0, 0);
-        }
-        if (ph.embed != nullptr && ph.h_out != nullptr && blockIdx.x == 0) {
-          // the raw embedding row is the residual stream of layer 0 (read by o_proj's epilogue)
-#pragma unroll
-          for (int u = 0; u < XU; ++u) {
-            const int c = tid + u * TC_CONSUMERS;
-            if (c < nch) *reinterpret_cast<uint4*>(ph.h_out + (long long)b * K + c * 8) = xv[u];
-          }
-        }
-        if (ph.norm_w != nullptr) {
-          ss = 0.f;
-#pragma unroll
-          for (int u = 0; u < XU; ++u) {
-            const uint4 v = xv[u];
-            const float f0 = bf16lo(v.x), f1 = bf16hi(v.x), f2 = bf16lo(v.y), f3 = bf16hi(v.y);
-            const float f4 = bf16lo(v.z), f5 = bf16hi(v.z), f6 = bf16lo(v.w), f7 = bf16hi(v.w);
-            ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
-          }
-          ss = warp_sum(ss);
-          if (b > 0) cbar();                          // red[] of the previous clip has been read
-          if (lane == 0) red[warp] = ss;
-          cbar();
-          float tot = 0.f;
-#pragma unroll
-          for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
-          const float rstd = rsqrtf(tot / (float)K + p.eps);
-#pragma unroll
-          for (int u = 0; u < XU; ++u) {
-            const int c = tid + u * TC_CONSUMERS;
-            if (c < nch) {
-              const uint4 v = xv[u];
-              const uint4 gw = *reinterpret_cast<const uint4*>(xb + c * 8);
-              uint4 o;
-              // w * bf16(x * rstd), the product rounded to bf16 again (LlamaRMSNorm)
-              o.x = bf16x2_mul(gw.x, pack_bf16x2(bf16lo(v.x) * rstd, bf16hi(v.x) * rstd));
-              o.y = bf16x2_mul(gw.y, pack_bf16x2(bf16lo(v.y) * rstd, bf16hi(v.y) * rstd));
-              o.z = bf16x2_mul(gw.z, pack_bf16x2(bf16lo(v.z) * rstd, bf16hi(v.z) * rstd));
-              o.w = bf16x2_mul(gw.w, pack_bf16x2(bf16lo(v.w) * rstd, bf16hi(v.w) * rstd));
-              *reinterpret_cast<uint4*>(xb + c * 8) = o;
-            }
+            tok[b] = bi[b];
+            if (b < NB && blockIdx.x == 0 && tid == 0 && ph.tok_out != nullptr) ph.tok_out[(long long)b * ph.tok_out_stride] = tok[b];
           }
         } else {
 #pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (b < NB) asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(tok[b]) : "l"(ph.tok_in + (long long)b * ph.tok_stride) : "memory");
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int t = tok[b] < 0 ? 0 : (tok[b] >= ph.vocab ? ph.vocab - 1 : tok[b]);
+          xg[b] = ph.embed + (long long)t * K;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b < NB) {
+#pragma unroll
           for (int u = 0; u < XU; ++u) {
             const int c = tid + u * TC_CONSUMERS;
-            if (c < nch) *reinterpret_cast<uint4*>(xb + c * 8) = xv[u];
+            if (c < nch)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xs + (size_t)b * K + c * 8)), "l"(xg[b] + c * 8) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      // from here on every thread touches only the chunks it copied itself, until the barrier
+      if (ph.embed != nullptr && ph.h_out != nullptr && blockIdx.x == 0) {
+        for (int b = 0; b < NB; ++b) {
+#pragma unroll
+          for (int u = 0; u < XU; ++u) {
+            const int c = tid + u * TC_CONSUMERS;
+            if (c < nch) *reinterpret_cast<uint4*>(ph.h_out + (long long)b * K + c * 8) = *reinterpret_cast<const uint4*>(xs + (size_t)b * K + c * 8);
+          }
+        }
+      }
+      if (ph.norm_w != nullptr) {
+        float ssb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b < NB) {
+            // the same per-thread, per-warp and cross-warp summation order as the single-clip path
+#pragma unroll
+            for (int u = 0; u < XU; ++u) {
+              const int c = tid + u * TC_CONSUMERS;
+              const uint4 v = (c < nch) ? *reinterpret_cast<const uint4*>(xs + (size_t)b * K + c * 8) : make_uint4(0, 0, 0, 0);
+              const float f0 = bf16lo(v.x), f1 = bf16hi(v.x), f2 = bf16lo(v.y), f3 = bf16hi(v.y);
+              const float f4 = bf16lo(v.z), f5 = bf16hi(v.z), f6 = bf16lo(v.w), f7 = bf16hi(v.w);
+              ssb[b] += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
+            }
+            ssb[b] = warp_sum(ssb[b]);
+            if (lane == 0) red[b * TC_CWARPS + warp] = ssb[b];
+          }
+        }
+        cbar();
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b < NB) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < TC_CWARPS; ++w) tot += red[b * TC_CWARPS + w];
+            const float rstd = rsqrtf(tot / (float)K + p.eps);
+#pragma unroll
+            for (int u = 0; u < XU; ++u) {
+              const int c = tid + u * TC_CONSUMERS;
+              if (c < nch) {
+                uint4* px = reinterpret_cast<uint4*>(xs + (size_t)b * K + c * 8);
+                const uint4 v = *px;
+                const uint4 gwu = *reinterpret_cast<const uint4*>(nw + c * 8);
+                uint4 o;
+                o.x = bf16x2_mul(gwu.x, pack_bf16x2(bf16lo(v.x) * rstd, bf16hi(v.x) * rstd));
+                o.y = bf16x2_mul(gwu.y, pack_bf16x2(bf16lo(v.y) * rstd, bf16hi(v.y) * rstd));
+                o.z = bf16x2_mul(gwu.z, pack_bf16x2(bf16lo(v.z) * rstd, bf16hi(v.z) * rstd));
+                o.w = bf16x2_mul(gwu.w, pack_bf16x2(bf16lo(v.w) * rstd, bf16hi(v.w) * rstd));
+                *px = o;
+              }
+            }
           }
         }
       }
       cbar();
+    } else {
+      if (ph.norm_w != nullptr) {
+        for (int b = 0; b < NB; ++b) {
+  #pragma unroll
+          for (int u = 0; u < XU; ++u) {
+            const int c = tid + u * TC_CONSUMERS;
+            if (c < nch) *reinterpret_cast<uint4*>(xs + (size_t)b * K + c * 8) = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + c * 8));
+          }
+        }
+      }
+      float ss = 0.f;
+      if (i == 0) {
+        pdl_wait();                                    // the first activation vector comes from the previous kernel
+        if (tid == 0) trace(i, 1);
+        for (int b = 0; b < NB; ++b) {                  // one clip after the other (one L2 round trip each)
+          bf16* xb = xs + (size_t)b * K;
+          const bf16* xg = ph.x + (long long)b * ph.ldx;
+          if (ph.embed != nullptr) {
+            // fused token-embedding gather: x = embed[token]. The token is either given (first step
+            // of a decode loop) or the arg-max of the previous step's logits, whose per-CTA partials
+            // every warp reduces for itself (same result in every warp: no barrier needed)
+            int tok;
+            if (ph.amax_in != nullptr) {
+              float bv = -INFINITY; int bi = 0x7fffffff;
+              for (int c = lane; c < ph.amax_n; c += 32) {
+                float v; int ix;
+                asm volatile("ld.global.cg.v2.b32 {%0,%1}, [%2];" : "=f"(v), "=r"(ix) : "l"(ph.amax_in + (size_t)c * NB + b) : "memory");
+                if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+              }
+  #pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+              }
+              tok = bi;
+              if (blockIdx.x == 0 && tid == 0 && ph.tok_out != nullptr) ph.tok_out[(long long)b * ph.tok_out_stride] = tok;
+            } else {
+              asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(tok) : "l"(ph.tok_in + (long long)b * ph.tok_stride) : "memory");
+            }
+            tok = tok < 0 ? 0 : (tok >= ph.vocab ? ph.vocab - 1 : tok);
+            xg = ph.embed + (long long)tok * K;
+          }
+          uint4 xv[XU];
+  #pragma unroll
+          for (int u = 0; u < XU; ++u) {
+            const int c = tid + u * TC_CONSUMERS;
+            xv[u] = (c < nch) ? ld_cg_v4(xg + c * 8) : make_uint4(0, 0, 0, 0);
+          }
+          if (ph.embed != nullptr && ph.h_out != nullptr && blockIdx.x == 0) {
+            // the raw embedding row is the residual stream of layer 0 (read by o_proj's epilogue)
+  #pragma unroll
+            for (int u = 0; u < XU; ++u) {
+              const int c = tid + u * TC_CONSUMERS;
+              if (c < nch) *reinterpret_cast<uint4*>(ph.h_out + (long long)b * K + c * 8) = xv[u];
+            }
+          }
+          if (ph.norm_w != nullptr) {
+            ss = 0.f;
+  #pragma unroll
+            for (int u = 0; u < XU; ++u) {
+              const uint4 v = xv[u];
+              const float f0 = bf16lo(v.x), f1 = bf16hi(v.x), f2 = bf16lo(v.y), f3 = bf16hi(v.y);
+              const float f4 = bf16lo(v.z), f5 = bf16hi(v.z), f6 = bf16lo(v.w), f7 = bf16hi(v.w);
+              ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
+            }
+            ss = warp_sum(ss);
+            if (b > 0) cbar();                          // red[] of the previous clip has been read
+            if (lane == 0) red[warp] = ss;
+            cbar();
+            float tot = 0.f;
+  #pragma unroll
+            for (int w = 0; w < TC_CWARPS; ++w) tot += red[w];
+            const float rstd = rsqrtf(tot / (float)K + p.eps);
+  #pragma unroll
+            for (int u = 0; u < XU; ++u) {
+              const int c = tid + u * TC_CONSUMERS;
+              if (c < nch) {
+                const uint4 v = xv[u];
+                const uint4 gw = *reinterpret_cast<const uint4*>(xb + c * 8);
+                uint4 o;
+                // w * bf16(x * rstd), the product rounded to bf16 again (LlamaRMSNorm)
+                o.x = bf16x2_mul(gw.x, pack_bf16x2(bf16lo(v.x) * rstd, bf16hi(v.x) * rstd));
+                o.y = bf16x2_mul(gw.y, pack_bf16x2(bf16lo(v.y) * rstd, bf16hi(v.y) * rstd));
+                o.z = bf16x2_mul(gw.z, pack_bf16x2(bf16lo(v.z) * rstd, bf16hi(v.z) * rstd));
+                o.w = bf16x2_mul(gw.w, pack_bf16x2(bf16lo(v.w) * rstd, bf16hi(v.w) * rstd));
+                *reinterpret_cast<uint4*>(xb + c * 8) = o;
+              }
+            }
+          } else {
+  #pragma unroll
+            for (int u = 0; u < XU; ++u) {
+              const int c = tid + u * TC_CONSUMERS;
+              if (c < nch) *reinterpret_cast<uint4*>(xb + c * 8) = xv[u];
+            }
+          }
+        }
+        cbar();
+      }
     }
     if (tid == 0) trace(i, 2);
 
@@ -445,17 +573,19 @@ __global__ void gemv_tc_repack_kernel(const bf16* __restrict__ W, bf16* __restri
 
 // shared-memory plan for a chain of phases on `grid` CTAs; returns the slot count (0 = does not fit)
 int plan(const TcPhase* ph, int n, int nb, int grid, size_t* smem_bytes, int* x_elems, int* r_cap) {
-  int kmax = 0, rmax = 0, want = TC_DEFAULT_SLOTS;
+  int rmax = 0, want = TC_DEFAULT_SLOTS;
+  int xe = 0;                                        // x buffer: nb vectors (+ the parked norm weights when nb > 1)
   for (int i = 0; i < n; ++i) {
+    const int e = ph[i].K * (nb + ((nb > 1 && ph[i].norm_w != nullptr) ? 1 : 0));
+    xe = e > xe ? e : xe;
     const int n_groups = (ph[i].N + 15) / 16;
     if (n_groups < grid) return 0;                   // every CTA streams at least one row group
     if (ph[i].K % 32 != 0 || ph[i].K > 14336) return 0;
-    kmax = ph[i].K > kmax ? ph[i].K : kmax;
     if (ph[i].ring_slots > want) want = ph[i].ring_slots;
     const int r = ((n_groups + grid - 1) / grid) * 16;
     rmax = r > rmax ? r : rmax;
   }
-  const size_t fixed = (size_t)nb * kmax * 2 + (size_t)(2 * TC_CWARPS * 16 + rmax) * 4 * 4 + 16 * 4 + 2 * TC_MAX_SLOTS * 8 + 128;
+  const size_t fixed = (size_t)xe * 2 + (size_t)(2 * TC_CWARPS * 16 + rmax) * 4 * 4 + 4 * TC_CWARPS * 4 + 2 * TC_MAX_SLOTS * 8 + 128;
   static const int env_slots = getenv("VCL_GEMV_TC_SLOTS") ? atoi(getenv("VCL_GEMV_TC_SLOTS")) : 0;
   static const size_t budget = getenv("VCL_GEMV_TC_SMEM_KB") ? (size_t)atoi(getenv("VCL_GEMV_TC_SMEM_KB")) * 1024 : (size_t)TC_SMEM_BUDGET;
   if (fixed + 4 * (size_t)TC_SLOT_BYTES > (nb > 1 ? (size_t)212 * 1024 : budget)) return 0;
@@ -467,7 +597,7 @@ int plan(const TcPhase* ph, int n, int nb, int grid, size_t* smem_bytes, int* x_
   if (slots > want) slots = want;
   if (env_slots > 0 && env_slots < slots) slots = env_slots;
   *smem_bytes = (size_t)slots * TC_SLOT_BYTES + fixed;
-  *x_elems = nb * kmax; *r_cap = rmax;
+  *x_elems = xe; *r_cap = rmax;
   return slots;
 }
 
