@@ -380,7 +380,8 @@ attn_vit_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 template <bool FULL>
 __global__ void __launch_bounds__(T1_THREADS, 2)
 attn_vit_tc1p_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                     const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int C, int n_tiles) {
+                     const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int C, int n_tiles,
+                     unsigned long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
@@ -540,8 +541,18 @@ attn_vit_tc1p_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int t = tile & 1, h = (tile >> 1) % H, n = (tile >> 1) / H;
       const long long row0 = (long long)n * S;
       const bool do_tail = key256 && t == 1;
+      // optional phase stamps of the first 12 tiles of every CTA (tools/attn_trace.py); null in production
+      auto stamp = [&](int ev) {
+        if (trace != nullptr && tix == 0 && i < 12) {
+          unsigned long long t_;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+          trace[((size_t)blockIdx.x * 12 + i) * 8 + ev] = t_;
+        }
+      };
+      stamp(0);
       mbar_wait_safe(BAR(B_QK), ph);
       mbar_wait_safe(BAR(B_ROW), ph);
+      stamp(1);
       if (key256) {
         if (tix < 128) sm->s256[tix] = bf16r(dot64(smem + T1_OFF_Q, tix, sm->k256)) * SCALE;
         if (do_tail) sm->tsc[tix] = bf16r(dot64(smem + T1_OFF_K, tix, sm->q256)) * SCALE;
@@ -553,6 +564,7 @@ attn_vit_tc1p_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int n_valid = FULL ? 128 : max(0, min(128, S - hf * 128));
       mbar_wait_safe(BAR(B_S), ph);
       tc_fence_after();
+      stamp(2);
       uint32_t st[64];
       __nv_bfloat162 mx2 = __float2bfloat162_rn(-INFINITY);
 #pragma unroll
@@ -575,6 +587,7 @@ attn_vit_tc1p_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       sm->smax[hf][r] = fmaxf(__low2float(mx2), __high2float(mx2)) * SCALE;
       named_bar_sync(1, T1_SM_THREADS);                       // also: all Q / K row reads are done
+      stamp(3);
       const float m = fmaxf(fmaxf(sm->smax[0][r], sm->smax[1][r]), sm->s256[r]);
       const float mb = m * LOG2E;
       const float p256 = key256 ? ex2_approx(sm->s256[r] * LOG2E - mb) : 0.f;
@@ -602,8 +615,10 @@ attn_vit_tc1p_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       mbar_arrive(BAR(B_P));
+      stamp(4);
       mbar_wait_safe(BAR(B_O), ph);
       tc_fence_after();
+      stamp(5);
       uint32_t v[32];
       __syncwarp();
       tmem_ld_32x32(tmem + ((uint32_t)(q4 * 32) << 16) + hf * 32, v);
@@ -627,6 +642,7 @@ attn_vit_tc1p_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       tc_fence_before();
       mbar_arrive(BAR(B_EPI));
+      stamp(6);
     }
   }
 
@@ -663,13 +679,13 @@ int launch_attention_vit_tc(const bf16* qkv, bf16* out, int n_frames, int S, int
   static const bool one_shot = getenv("VCL_ATTN_ONE_SHOT") != nullptr;   // A/B: one CTA per tile instead of persistent CTAs
   const int n_tiles = n_frames * H * 2;
   const int grid = n_tiles < 2 * device_num_sms() ? n_tiles : 2 * device_num_sms();
-  if (one_shot || g_attn_trace != nullptr) {
+  if (one_shot) {
     if (S >= 256) attn_vit_tc1_kernel<true><<<n_tiles, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, g_attn_trace);
     else attn_vit_tc1_kernel<false><<<n_tiles, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, g_attn_trace);
   } else if (S >= 256) {
-    attn_vit_tc1p_kernel<true><<<grid, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, n_tiles);
+    attn_vit_tc1p_kernel<true><<<grid, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, n_tiles, g_attn_trace);
   } else {
-    attn_vit_tc1p_kernel<false><<<grid, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, n_tiles);
+    attn_vit_tc1p_kernel<false><<<grid, T1_THREADS, T1_SMEM, stream>>>(tq, tm, qkv, out, S, H, C, n_tiles, g_attn_trace);
   }
   VCL_CUDA_OK(cudaGetLastError());
   count_launches(1);
