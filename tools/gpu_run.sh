@@ -13,7 +13,7 @@
 #   launches         ncu launch list (gpu__time_duration) of tools/profile_step.py -> launches.csv
 #   ncufull:<regex>  ncu --set full on the kernels matching <regex> in tools/profile_step.py -> ncu_full_<regex>.csv
 #                    (the .ncu-rep stays in /tmp on the box: gpurun copies back at most 64 MiB)
-#   sweep            tools/sweep_gemm.py                             -> gemm_sweep.txt
+#   sweep[:ENV=V,..] tools/sweep_gemm.py under the given environment       -> gemm_sweep<env>.txt
 #   micro:<what>     tools/microbench.py <what>                      -> micro_<what>.txt
 #   py:<script>      python tools/<script>.py, 300 s cap                  -> py_<script>.txt
 #   sass             cuobjdump opcode histogram per kernel           -> sass_summary.txt
@@ -41,7 +41,7 @@ for stage in "$@"; do
     ncufull)
       PROF_LLM_LAYERS=${PROF_LLM_LAYERS:-2} timeout -s KILL 1500 ncu --set full --clock-control none --import-source on -k "regex:$arg" -c ${NCU_COUNT:-12} -s ${NCU_SKIP:-0} -o "/tmp/ncu_full_$tag" -f python tools/profile_step.py > "gpurun_out/ncu_full_$tag.log" 2>&1; echo "ncu exit $?"
       ncu -i "/tmp/ncu_full_$tag.ncu-rep" --page raw --csv > "gpurun_out/ncu_full_$tag.raw.csv" 2>/dev/null; python tools/ncu_summary.py "gpurun_out/ncu_full_$tag.raw.csv" > "gpurun_out/ncu_full_$tag.csv"; head -n 6 "gpurun_out/ncu_full_$tag.csv" ;;
-    sweep) timeout -s KILL 900 python tools/sweep_gemm.py > gpurun_out/gemm_sweep.txt 2>&1; echo "sweep exit $?"; cat gpurun_out/gemm_sweep.txt ;;
+    sweep) env $(echo "$arg" | tr ',' ' ') timeout -s KILL 900 python tools/sweep_gemm.py > "gpurun_out/gemm_sweep$tag.txt" 2>&1; echo "sweep exit $?"; cat "gpurun_out/gemm_sweep$tag.txt" ;;
     micro) timeout -s KILL 900 python tools/microbench.py $(echo "$arg" | tr ',' ' ') > "gpurun_out/micro_$tag.txt" 2>&1; echo "micro exit $?"; tail -n 40 "gpurun_out/micro_$tag.txt" ;;
     ab) echo "$arg $(env $(echo "$arg" | tr ',' ' ') timeout -s KILL 150 python bench.py --no-cpu --no-library --steps ${AB_STEPS:-8} 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],3), {k: round(v,2) for k,v in d['stages'].items() if k.endswith('_ms')})" 2>&1 | tail -n 1)" | tee -a gpurun_out/ab.txt ;;
     py) timeout -s KILL 300 python "tools/$arg.py" > "gpurun_out/py_$tag.txt" 2>&1; echo "py exit $?"; tail -n 30 "gpurun_out/py_$tag.txt" ;;

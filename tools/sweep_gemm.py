@@ -9,7 +9,7 @@ def timeit(fn, iters=8, warm=2):
     for _ in range(warm): fn()
     ts = []
     for _ in range(iters):
-        flush.zero_()
+        if not os.environ.get("SWEEP_NOFLUSH"): flush.zero_()      # SWEEP_NOFLUSH=1: operands stay in L2 between runs
         s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
         s.record(); fn(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
     ts.sort(); return ts[len(ts) // 2]
@@ -18,7 +18,10 @@ SHAPES = [("vit_qkv", 25700, 3072, 1024, vn.ACT_NONE), ("vit_out", 25700, 1024, 
           ("pre_qkv", 448, 12288, 4096, vn.ACT_NONE), ("pre_o", 448, 4096, 4096, vn.ACT_NONE),
           ("pre_gu", 448, 22016, 4096, vn.ACT_SWIGLU), ("pre_down", 448, 4096, 11008, vn.ACT_NONE),
           ("pre16_qkv", 7168, 12288, 4096, vn.ACT_NONE)]
+only = os.environ.get("SWEEP_SHAPES")        # name prefix filter, e.g. SWEEP_SHAPES=pre
+print("VCL_GEMM_PF =", os.environ.get("VCL_GEMM_PF", "(default)"), flush=True)
 for name, M, N, K, act in SHAPES:
+    if only and not name.startswith(only): continue
     a = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
     out = torch.zeros(M, N // 2 if act == vn.ACT_SWIGLU else N, device=dev, dtype=torch.bfloat16)
     res = []

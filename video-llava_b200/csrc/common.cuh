@@ -130,6 +130,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
       : "memory");
 }
 
+// 2-D tile global -> L2 only (no shared memory, no barrier): runs a weight stream ahead of the smem ring
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // same, multicast: the tile lands at the same shared-memory offset of every CTA in cta_mask and
 // completes tx bytes on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst_smem, const void* tmap, uint32_t bar,

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(384, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, bf16* C, long long ldc,
                     const bf16* __restrict__ bias, const bf16* residual, long long ldr, int M,
-                    int N, int K) {
+                    int N, int K, int pf_ahead) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -252,9 +252,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // L2 look-ahead for the weight operand: with few row tiles (prefill, M = 448) the weights come from
+      // HBM and the ring alone holds few of this CTA's own weight bytes in flight (4 stages x an 8 KB multicast
+      // slice). A prefetch cursor runs pf_ahead k-blocks in front of the loads, across tile boundaries; the
+      // launcher turns it on only where it measured faster (weight_prefetch_depth).
+      int pf_tile = cluster_id, pf_kb = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile < num_tiles) {
+          tma_prefetch_2d(&tmap_b, pf_kb * Cfg::BLOCK_K, (pf_tile % num_n) * BLOCK_N + cta_rank * B_SLICE_ROWS);
+          if (++pf_kb == num_k) { pf_kb = 0; pf_tile += n_clusters; }
+        }
+      };
+      for (int i = 0; i < pf_ahead; ++i) prefetch_next();
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
         for (int kb = 0; kb < num_k; ++kb) {
+          if (pf_ahead > 0) prefetch_next();
           mbar_wait(empty_bar(stage), phase ^ 1u);    // slot free in EVERY CTA of the cluster
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
@@ -364,7 +377,7 @@ template <int BLOCK_N, int ACT>
 __global__ void __launch_bounds__(384, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, bf16* C,
                      long long ldc, const bf16* __restrict__ bias, const bf16* residual, long long ldr, int M, int N,
-                     int K, unsigned long long* __restrict__ trace) {
+                     int K, int pf_ahead, unsigned long long* __restrict__ trace) {
   // debug timeline (tools/gemm_pair_trace.py): [cta < 2][k-block < 128][4] globaltimer stamps; null in production
   auto stamp = [&](int kbi, int ev) {
     if (trace != nullptr && blockIdx.x < 2 && kbi < 128) {
@@ -423,9 +436,18 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int pf_tile = cluster_id, pf_kb = 0;                   // L2 look-ahead for this CTA's half of the weight tiles
+      auto prefetch_next = [&]() {
+        if (pf_tile < num_tiles) {
+          tma_prefetch_2d(&tmap_b, pf_kb * 64, (pf_tile % num_n) * BLOCK_N + (int)rank * (BLOCK_N / 2));
+          if (++pf_kb == num_k) { pf_kb = 0; pf_tile += n_clusters; }
+        }
+      };
+      for (int i = 0; i < pf_ahead; ++i) prefetch_next();
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int m_blk = (tile / num_n) * 2 + (int)rank, n_blk = tile % num_n;
         for (int kb = 0; kb < num_k; ++kb) {
+          if (pf_ahead > 0) prefetch_next();
           stamp(kb, 0);
           mbar_wait_safe(empty_bar(stage), phase ^ 1u);
           stamp(kb, 1);
@@ -547,6 +569,17 @@ int device_num_sms() {
   return g_num_sms;
 }
 
+// k-blocks of L2 look-ahead for the weight operand (see the producer), measured on the prefill shapes
+// (M = 448, tools/sweep_gemm.py with VCL_GEMM_PF = 0 / 8 / 16 / 32): it pays only where one CTA of a 4-cluster
+// streams its quarter of a 256-wide weight tile -- gate|up 95 -> 88 us at depth 8, q|k|v 71 -> 65 us (level with
+// the 128-wide tiles it then uses anyway) -- is neutral for the CTA pairs and costs 5-10 % where every row tile
+// prefetches the same weights for itself (no cluster). VCL_GEMM_PF=<k-blocks> overrides (0 = off) for A/B runs.
+static int weight_prefetch_depth(const GemmArgs& g, int block_n, int cl) {
+  static const int forced = getenv("VCL_GEMM_PF") ? atoi(getenv("VCL_GEMM_PF")) : -1;
+  if (forced >= 0) return forced;
+  return (cl == 4 && block_n == 256 && (g.M + 127) / 128 <= 16) ? 8 : 0;
+}
+
 template <int BLOCK_N, int ACT>
 static int launch_pair(const GemmArgs& g, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BLOCK_N>;
@@ -570,7 +603,7 @@ static int launch_pair(const GemmArgs& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.C, (long long)g.ldc, g.bias, g.residual, (long long)g.ldr, g.M,
-                                 g.N, g.K, g_gemm_trace));
+                                 g.N, g.K, weight_prefetch_depth(g, BLOCK_N, -2), g_gemm_trace));
   count_launches(1);
   return 0;
 }
@@ -613,7 +646,7 @@ static int launch_one(const GemmArgs& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
   VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.C, (long long)g.ldc, g.bias, g.residual,
-                                 (long long)g.ldr, g.M, g.N, g.K));
+                                 (long long)g.ldr, g.M, g.N, g.K, weight_prefetch_depth(g, BLOCK_N, CL)));
   count_launches(1);
   return 0;
 }
