@@ -122,7 +122,11 @@ def test_layernorm_rmsnorm(rows, D):
 
 @pytest.mark.parametrize("B,S,H,hd,causal", [(3, 257, 16, 64, False), (2, 448, 4, 128, True),
                                              (1, 64, 2, 128, True), (5, 577, 2, 64, False),
-                                             (1, 100, 3, 128, True)])
+                                             (1, 100, 3, 128, True),
+                                             # causal hd 128 up to 512 keys: the tcgen05 prefill kernel (1..4 key blocks,
+                                             # ragged last tile, a single head / clip); 640 keys: the mma.sync kernel
+                                             (1, 512, 2, 128, True), (2, 129, 3, 128, True), (1, 300, 1, 128, True),
+                                             (3, 448, 32, 128, True), (1, 640, 2, 128, True)])
 def test_attention(B, S, H, hd, causal):
     torch.manual_seed(S + hd)
     dev = _dev()

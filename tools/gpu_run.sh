@@ -17,7 +17,7 @@
 #   micro:<what>     tools/microbench.py <what>                      -> micro_<what>.txt
 #   py:<script>      python tools/<script>.py, 300 s cap                  -> py_<script>.txt
 #   sass             cuobjdump opcode histogram per kernel           -> sass_summary.txt
-#   ab:<ENV=V,...>   bench.py --no-cpu --no-library under the given environment (A/B switches), 150 s cap -> ab.txt
+#   ab:<ENV=V,...>   bench.py --no-cpu --no-library $AB_ARGS under the given environment (A/B switches), 150 s cap -> ab.txt
 # Every stage runs under its own `timeout`: a hung kernel costs minutes, not the whole GPU budget.
 set -u
 mkdir -p gpurun_out
@@ -43,7 +43,7 @@ for stage in "$@"; do
       ncu -i "/tmp/ncu_full_$tag.ncu-rep" --page raw --csv > "gpurun_out/ncu_full_$tag.raw.csv" 2>/dev/null; python tools/ncu_summary.py "gpurun_out/ncu_full_$tag.raw.csv" > "gpurun_out/ncu_full_$tag.csv"; head -n 6 "gpurun_out/ncu_full_$tag.csv" ;;
     sweep) env $(echo "$arg" | tr ',' ' ') timeout -s KILL 900 python tools/sweep_gemm.py > "gpurun_out/gemm_sweep$tag.txt" 2>&1; echo "sweep exit $?"; cat "gpurun_out/gemm_sweep$tag.txt" ;;
     micro) timeout -s KILL 900 python tools/microbench.py $(echo "$arg" | tr ',' ' ') > "gpurun_out/micro_$tag.txt" 2>&1; echo "micro exit $?"; tail -n 40 "gpurun_out/micro_$tag.txt" ;;
-    ab) echo "$arg $(env $(echo "$arg" | tr ',' ' ') timeout -s KILL 150 python bench.py --no-cpu --no-library --steps ${AB_STEPS:-8} 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],3), {k: round(v,2) for k,v in d['stages'].items() if k.endswith('_ms')})" 2>&1 | tail -n 1)" | tee -a gpurun_out/ab.txt ;;
+    ab) echo "$arg $(env $(echo "$arg" | tr ',' ' ') timeout -s KILL 150 python bench.py --no-cpu --no-library --steps ${AB_STEPS:-8} ${AB_ARGS:-} 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value'],3), {k: round(v,2) for k,v in d['stages'].items() if k.endswith('_ms')})" 2>&1 | tail -n 1)" | tee -a gpurun_out/ab.txt ;;
     py) timeout -s KILL 300 python "tools/$arg.py" > "gpurun_out/py_$tag.txt" 2>&1; echo "py exit $?"; tail -n 30 "gpurun_out/py_$tag.txt" ;;
     sass) python tools/sass_summary.py > gpurun_out/sass_summary.txt 2>&1; tail -n 30 gpurun_out/sass_summary.txt ;;
     *) echo "unknown stage $stage" ;;

@@ -9,8 +9,9 @@
 //     multiplied by `scaling` (a second bf16 rounding), softmax runs in fp32 and is cast back to
 //     bf16 before the PV matmul. The score roundings are reproduced; the probabilities are rounded
 //     to bf16 un-normalised (flash form), the one place this kernel differs from eager by design.
-//     Round 1 uses the legacy tensor path here (attention is 4 % of the ViT flops and <1 % of the
-//     prefill flops); the tcgen05 version is the next step for this file.
+//     The hot path no longer comes here: the ViT's S = 257 runs in attention_tc.cu, the causal hd-128 prefill
+//     up to 512 keys in attention_prefill_tc.cu (both tcgen05). This kernel serves the other shapes: the
+//     336-px tower (S = 577), longer prompts, continued prefills beyond 512 keys.
 //
 // (2) the single-query decode attention lives in decode_attention.cu (cluster of 4 CTAs per head).
 #include "common.cuh"
@@ -252,7 +253,7 @@ int init_attention_kernels() {
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * 64 * 2));
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * 128 * 2));
   VCL_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * 128 * 2));
-  return 0;
+  return init_attention_prefill_tc_kernels();
 }
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
@@ -262,6 +263,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
                   a.v_sb % 8 == 0 && a.o_ss % 2 == 0 && a.o_sh % 2 == 0 && a.o_sb % 2 == 0,
               "attention: strides must keep 16-byte row alignment");
   if (a.B <= 0 || a.H <= 0 || a.S <= 0) return 0;
+  if (attention_prefill_tc_supported(a)) return launch_attention_prefill_tc(a, stream);   // LLaMA prefill up to 512 keys
   if (a.head_dim == 64) {
     return a.causal ? launch_attn_t<64, true>(a, stream) : launch_attn_t<64, false>(a, stream);
   }

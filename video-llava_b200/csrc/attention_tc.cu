@@ -1,8 +1,8 @@
 // CLIP ViT self-attention on the 5th-generation tensor cores (non-causal, head_dim 64, S = P+1).
 //
-// One CTA per (frame, head, 128-query tile), two CTAs per SM. The S x S problem is tiny (257 x 257 for
-// ViT-L/14 @224), so the whole K and V of the head live in shared memory and the scores of 128 queries x
-// 256 keys live in TMEM:
+// A work item is one 128-query tile of one (frame, head); two CTAs per SM. The S x S problem is tiny
+// (257 x 257 for ViT-L/14 @224), so the whole K and V of the head live in shared memory and the scores of
+// 128 queries x 256 keys live in TMEM:
 //
 //   warp 8 (1 thread)  TMA: Q tile [128 x 64], K, V tiles [256 rows x 64] of this (frame, head) straight
 //                      out of the fused qkv activation (128-B swizzle); then issues all tcgen05.mma:
@@ -15,12 +15,16 @@
 //                      and finally normalises and stores 32 O columns
 //   warp 9             TMEM allocator; softmax + PV of query row 256 (the 257th token)
 //
-// Measured alternatives (tools/experiments/): one CTA per (frame, head) with both tiles in 512 TMEM
-// columns (round 1: 119 us per layer against 97); a persistent CTA per SM that processes both tiles of
-// an item at once and prefetches the next item's Q / K (round 2: parity-green, 108 us against 95 -- the
-// per-CTA timeline of THIS kernel, tools/attn_trace.py, is 1.2 us set-up + 2.1 us TMA wait + 0.6 us S +
-// 0.25 us pass 1 + 1.7 us exp2 pass + 0.8 us P.V + 0.75 us epilogue = 7.4 us, and two co-resident CTAs
-// overlap each other's phases better than one CTA running its two tiles in lock-step).
+// Two kernels share this tile pipeline:
+//   attn_vit_tc1p_kernel  (default) persistent: 2 x #SMs CTAs walk the tile list; set-up once per CTA, the
+//                         next tile's Q | K are fetched while the current tile's epilogue runs
+//   attn_vit_tc1_kernel   one CTA per tile (VCL_ATTN_ONE_SHOT=1): 95 us per layer against 87-93 us
+// Per-tile timeline of the persistent kernel (tools/attn_trace.py, two CTAs sharing the SM): 0.8 us wait
+// for Q | K, 1.3 us row-256 dot products + wait for S, 0.4 us pass 1, 2.7 us exp2 pass, 1.1 us wait for
+// P.V, 1.2 us epilogue = 7.5 us per tile and CTA. Measured alternatives (tools/experiments/): one CTA per
+// (frame, head) with both tiles in 512 TMEM columns (round 1: 119 us per layer); a persistent CTA per SM
+// that runs both tiles of an item in lock-step (round 2: parity-green, 108 us -- two independent CTAs per
+// SM overlap each other's phases better).
 //
 // S = 257 = 2*128 + 1: the 257th KEY is folded in analytically (one extra 64-long dot product per
 // query row, added to the max / sum / output), and the 257th QUERY row is a 33k-MAC problem whose

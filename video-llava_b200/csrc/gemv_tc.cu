@@ -31,6 +31,8 @@
 //               KV append, SwiGLU, residual, logits) run once at the end.
 // Ring depth: 6 slots -> 79 ms per 31 decode steps (7B), 8 -> 74 ms, 9 -> 79 ms, 13 -> 81 ms; two
 // half-SM CTAs of consecutive kernels (6 slots each) -> 77-82 ms. 8 it is.
+// Deeper rings only for the kernels that are not followed by the attention kernel (round 2: 12 slots for
+// gate|up, 11 for down, 12 for the head) do not help either: 77.1 / 74.6 / 75.8 (all three) against 74.7-75.3 ms.
 // An L2 look-ahead (round 2: the producer issuing cp.async.bulk.prefetch.L2 for the 4 / 8 / 16 / 32 slots of
 // its share in front of the ring, to keep HBM streaming while the ring is full during a hand-off) made the
 // decode loop slower the further it ran ahead: 76.5 / 78.2 / 83.2 / 91.4 ms against 75.8 ms without.

@@ -91,8 +91,12 @@ struct AttnArgs {
   int S_kv = 0;      // number of keys (0: = S); > S when the queries continue a cached sequence
   int q_off = 0;     // absolute position of query 0 for the causal mask (S_kv - S for a continuation)
 };
-int launch_attention(const AttnArgs& a, cudaStream_t stream);
+int launch_attention(const AttnArgs& a, cudaStream_t stream);     // dispatches to the tcgen05 prefill kernel when it applies
 int init_attention_kernels();
+// ---- attention_prefill_tc.cu : tcgen05 causal attention (hd 128, <= 512 keys) -----------------------
+bool attention_prefill_tc_supported(const AttnArgs& a);
+int launch_attention_prefill_tc(const AttnArgs& a, cudaStream_t stream);
+int init_attention_prefill_tc_kernels();
 // ---- attention_tc.cu : tcgen05 attention for the ViT (hd 64, 129 <= S <= 257, non-causal) ----------
 int launch_attention_vit_tc(const bf16* qkv, bf16* out, int n_frames, int S, int H, int C,
                             cudaStream_t stream);
