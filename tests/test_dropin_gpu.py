@@ -106,7 +106,7 @@ def test_tower_pool_generate_like_the_reference_caller():
 @torch.no_grad()
 def test_generate_continue_second_turn():
     """Second turn about the same video through the KV cache (generate_continue): the tokens it
-    produces must be the ones a from-scratch generate() on the concatenated context produces."""
+    produces must be the ones a from-scratch pass over the concatenated context decides on."""
     lcfg = O.LlmCfg(hidden=512, inter=1024, heads=4, layers=2)
     m = _model(lcfg, 3, max_batch=1)
     m.load_state_dict(O.random_llm_state(lcfg, seed=23))
@@ -117,11 +117,26 @@ def test_generate_continue_second_turn():
     turn2 = m.generate_continue(q2, do_sample=False, max_new_tokens=5)
     assert turn2.shape == (1, 448 + 5 + 11 + 5)
     assert torch.equal(turn2[:, :453], turn1) and torch.equal(turn2[:, 453:464], q2)
-    scratch = m.generate(torch.cat([turn1, q2], 1), video_spatio_temporal_features=feats.unsqueeze(0),
-                         do_sample=False, max_new_tokens=5)
-    # same arithmetic up to the GEMM tiling of the prefill: identical tokens except at bf16 near-ties
-    assert (scratch[:, 464:] == turn2[:, 464:]).float().mean().item() >= 0.8
-    assert scratch[0, 464].item() == turn2[0, 464].item()
+    # The same context from scratch, teacher-forced with the continued turn's tokens (a free-running comparison
+    # says nothing after the first near-tie): the two paths share the arithmetic up to the GEMM / GEMV tiling
+    # that produced the cached rows, so every continued token must be the from-scratch arg-max wherever that
+    # arg-max is decided by >= 3 bf16 ulps, and one of the tied candidates otherwise.
+    n_strict = 0
+    for i in range(5):
+        ctx = turn2[:, :464 + i]
+        lg = m(input_ids=ctx, video_spatio_temporal_features=feats.unsqueeze(0)).logits[0, -1].float()
+        top = torch.topk(lg, 2)
+        ulp = top.values[0].abs().clamp_min(2 ** -6) * 2 ** -7
+        margin = ((top.values[0] - top.values[1]) / ulp).item()
+        gap = ((top.values[0] - lg[turn2[0, 464 + i]]) / ulp).item()
+        print(f"[dropin] second turn, token {i}: continued {turn2[0, 464 + i].item()} from-scratch arg-max "
+              f"{top.indices[0].item()} (margin {margin:.1f} ulps, continued token {gap:.1f} ulps below the top)")
+        if margin >= 3:
+            n_strict += 1
+            assert gap == 0, (i, margin, gap)
+        else:
+            assert gap < 3, (i, margin, gap)
+    assert n_strict >= 1
     m2 = _model(lcfg, 3, max_batch=1)
     with pytest.raises(ValueError, match="no previous generate"):
         m2.generate_continue(q2)

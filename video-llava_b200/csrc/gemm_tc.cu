@@ -59,6 +59,80 @@ __device__ __forceinline__ float act_silu(float g) {
   return bf16r(g / (1.0f + __expf(-g)));
 }
 
+// ACT_ROPE epilogue (kernels.h: RopeEpilogue). A 128-column block of the q|k|v output is one head; the RoPE
+// partner of column d is d + 64, which sits 64 TMEM columns further in the same lane, so a thread reads BOTH
+// 32-column chunks of its pairs and the rotation is thread-local: with 128-wide tiles the two warps of a lane
+// quarter split the head's 64 pairs (d in [32 hf, 32 hf + 32)), with 256-wide tiles each takes one head.
+// Arithmetic = rope_kv_prefill_kernel (elementwise.cu): x rounded to bf16, every product rounded, fp32 sum, one
+// final rounding (transformers/models/llama/modeling_llama.py:124-168).
+template <int BLOCK_N, class WaitFn, class ArriveFn>
+__device__ __forceinline__ void gemm_epilogue_rope(uint32_t tmem_acc, int q4, int hf, int lane, int m_blk, int n_blk,
+                                                   bf16* C, long long ldc, int M, const RopeEpilogue& rp,
+                                                   WaitFn wait_full, ArriveFn arrive_empty) {
+  if constexpr (BLOCK_N == 128 || BLOCK_N == 256) {
+    constexpr int UNITS = BLOCK_N / 128;
+    const int row = m_blk * 128 + q4 * 32 + lane;
+    const bool row_ok = row < M;
+    const int b = row / rp.S, s = row - b * rp.S;
+    const int pos = rp.start_pos + s;
+    wait_full();
+    const uint32_t tl = tmem_acc + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll
+    for (int u = 0; u < UNITS; ++u) {
+      const int hh = BLOCK_N == 128 ? 0 : hf;                 // head inside the tile
+      const int d0 = 32 * (BLOCK_N == 128 ? hf : u);          // first pair of this unit
+      uint32_t lo[32], hi[32];
+      __syncwarp();
+      tmem_ld_32x32(tl + hh * 128 + d0, lo);
+      tmem_ld_32x32(tl + hh * 128 + 64 + d0, hi);
+      tc_wait_ld();
+      if (u == UNITS - 1) arrive_empty();                     // every TMEM read of this accumulator has completed
+      if (row_ok) {
+        const int gh = n_blk * UNITS + hh;                    // head index over q | k | v
+        const int which = gh / rp.H, head = gh - which * rp.H;
+        const long long coff = (((long long)b * rp.H + head) * rp.s_max + pos) * 128 + d0;
+        uint32_t olo[16], ohi[16];
+        if (which == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            olo[j] = pack_bf16x2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
+            ohi[j] = pack_bf16x2(__uint_as_float(hi[2 * j]), __uint_as_float(hi[2 * j + 1]));
+          }
+        } else {
+          const bf16* ct = rp.cos_t + (long long)pos * 64 + d0;
+          const bf16* st = rp.sin_t + (long long)pos * 64 + d0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(ct + q * 8));
+            const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(st + q * 8));
+            const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w}, sw[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = q * 4 + e;                        // pair of columns 2j, 2j + 1
+              const uint32_t l2 = pack_bf16x2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
+              const uint32_t h2 = pack_bf16x2(__uint_as_float(hi[2 * j]), __uint_as_float(hi[2 * j + 1]));
+              const float l0 = bf16lo(l2), l1 = bf16hi(l2), h0 = bf16lo(h2), h1 = bf16hi(h2);
+              const float c0 = bf16lo(cw[e]), c1 = bf16hi(cw[e]), s0 = bf16lo(sw[e]), s1 = bf16hi(sw[e]);
+              olo[j] = pack_bf16x2(bf16r(l0 * c0) + bf16r(-h0 * s0), bf16r(l1 * c1) + bf16r(-h1 * s1));
+              ohi[j] = pack_bf16x2(bf16r(h0 * c0) + bf16r(l0 * s0), bf16r(h1 * c1) + bf16r(l1 * s1));
+            }
+          }
+        }
+        bf16* dst = which == 0 ? C + (long long)row * ldc + gh * 128 + d0
+                               : (which == 1 ? rp.kcache : rp.vcache) + coff;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(olo[4 * q], olo[4 * q + 1], olo[4 * q + 2], olo[4 * q + 3]);
+          *reinterpret_cast<uint4*>(dst + 64 + q * 8) = make_uint4(ohi[4 * q], ohi[4 * q + 1], ohi[4 * q + 2], ohi[4 * q + 3]);
+        }
+      }
+    }
+  } else {
+    wait_full();               // narrower tiles are never launched with ACT_ROPE (launch_gemm_bf16_tn)
+    arrive_empty();
+  }
+}
+
 // One output tile of the epilogue, for the 32 rows x (BLOCK_N / 2) columns this warp owns: TMEM -> bias /
 // activation / residual -> bf16 -> global. warp w reads TMEM lanes 32*(w%4).. (hardware restriction) and
 // owns one half (hf) of the tile's 32-column chunks; the tcgen05.ld and the residual loads of chunk i+1
@@ -68,7 +142,11 @@ template <int BLOCK_N, int ACT, class WaitFn, class ArriveFn>
 __device__ __forceinline__ void gemm_epilogue_tile(uint32_t tmem_acc, int q4, int hf, int lane, int m_blk, int n_blk,
                                                    bf16* C, long long ldc, const bf16* __restrict__ bias,
                                                    const bf16* residual, long long ldr, int M, int N,
-                                                   WaitFn wait_full, ArriveFn arrive_empty) {
+                                                   const RopeEpilogue& rope, WaitFn wait_full, ArriveFn arrive_empty) {
+  if constexpr (ACT == ACT_ROPE) {
+    gemm_epilogue_rope<BLOCK_N>(tmem_acc, q4, hf, lane, m_blk, n_blk, C, ldc, M, rope, wait_full, arrive_empty);
+    return;
+  }
   constexpr int CH = BLOCK_N / 32;
   constexpr int PER = (CH + 1) / 2;
   const int c_begin = hf * PER;
@@ -192,7 +270,7 @@ __global__ void __launch_bounds__(384, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, bf16* C, long long ldc,
                     const bf16* __restrict__ bias, const bf16* residual, long long ldr, int M,
-                    int N, int K, int pf_ahead) {
+                    int N, int K, int pf_ahead, const RopeEpilogue rope) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -330,7 +408,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
       const int m_blk = (tile / num_n) * CL + cta_rank, n_blk = tile % num_n;
       gemm_epilogue_tile<BLOCK_N, ACT>(
-          tmem_base + acc * BLOCK_N, q4, hf, lane, m_blk, n_blk, C, ldc, bias, residual, ldr, M, N,
+          tmem_base + acc * BLOCK_N, q4, hf, lane, m_blk, n_blk, C, ldc, bias, residual, ldr, M, N, rope,
           [&]() { mbar_wait(tfull_bar(acc), acc_phase); tc_fence_after(); },
           [&]() { tc_fence_before(); mbar_arrive(tempty_bar(acc)); });
       acc ^= 1;
@@ -377,7 +455,7 @@ template <int BLOCK_N, int ACT>
 __global__ void __launch_bounds__(384, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, bf16* C,
                      long long ldc, const bf16* __restrict__ bias, const bf16* residual, long long ldr, int M, int N,
-                     int K, int pf_ahead, unsigned long long* __restrict__ trace) {
+                     int K, int pf_ahead, unsigned long long* __restrict__ trace, const RopeEpilogue rope) {
   // debug timeline (tools/gemm_pair_trace.py): [cta < 2][k-block < 128][4] globaltimer stamps; null in production
   auto stamp = [&](int kbi, int ev) {
     if (trace != nullptr && blockIdx.x < 2 && kbi < 128) {
@@ -501,7 +579,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int m_blk = (tile / num_n) * 2 + (int)rank, n_blk = tile % num_n;
       const uint32_t lead_tempty = mapa_cluster(tempty_bar(acc), 0);
       gemm_epilogue_tile<BLOCK_N, ACT>(
-          tmem_base + acc * BLOCK_N, q4, hf, lane, m_blk, n_blk, C, ldc, bias, residual, ldr, M, N,
+          tmem_base + acc * BLOCK_N, q4, hf, lane, m_blk, n_blk, C, ldc, bias, residual, ldr, M, N, rope,
           [&]() { mbar_wait_safe(tfull_bar(acc), acc_phase); tc_fence_after(); },
           [&]() { tc_fence_before(); mbar_arrive_cluster(lead_tempty); });
       acc ^= 1;
@@ -603,7 +681,7 @@ static int launch_pair(const GemmArgs& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.C, (long long)g.ldc, g.bias, g.residual, (long long)g.ldr, g.M,
-                                 g.N, g.K, weight_prefetch_depth(g, BLOCK_N, -2), g_gemm_trace));
+                                 g.N, g.K, weight_prefetch_depth(g, BLOCK_N, -2), g_gemm_trace, g.rope));
   count_launches(1);
   return 0;
 }
@@ -615,6 +693,7 @@ static int launch_pair_act(const GemmArgs& g, cudaStream_t stream) {
     case ACT_QGELU: return launch_pair<BLOCK_N, ACT_QGELU>(g, stream);
     case ACT_GELU: return launch_pair<BLOCK_N, ACT_GELU>(g, stream);
     case ACT_SWIGLU: return launch_pair<BLOCK_N, ACT_SWIGLU>(g, stream);
+    case ACT_ROPE: return launch_pair<BLOCK_N, ACT_ROPE>(g, stream);
   }
   set_last_error("gemm: unknown activation %d", g.act);
   return -1;
@@ -646,7 +725,7 @@ static int launch_one(const GemmArgs& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
   VCL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.C, (long long)g.ldc, g.bias, g.residual,
-                                 (long long)g.ldr, g.M, g.N, g.K, weight_prefetch_depth(g, BLOCK_N, CL)));
+                                 (long long)g.ldr, g.M, g.N, g.K, weight_prefetch_depth(g, BLOCK_N, CL), g.rope));
   count_launches(1);
   return 0;
 }
@@ -667,6 +746,9 @@ static int launch_act(const GemmArgs& g, int cl, cudaStream_t stream) {
     case ACT_QGELU: return launch_cl<BLOCK_N, ACT_QGELU>(g, cl, stream);
     case ACT_GELU: return launch_cl<BLOCK_N, ACT_GELU>(g, cl, stream);
     case ACT_SWIGLU: return launch_cl<BLOCK_N, ACT_SWIGLU>(g, cl, stream);
+    case ACT_ROPE:
+      if constexpr (BLOCK_N >= 128) return launch_cl<BLOCK_N, ACT_ROPE>(g, cl, stream);
+      break;
   }
   set_last_error("gemm: unknown activation %d", g.act);
   return -1;
@@ -691,6 +773,9 @@ template <int BLOCK_N>
 static int init_bn() {
   if (init_one<BLOCK_N, ACT_NONE>() || init_one<BLOCK_N, ACT_QGELU>() ||
       init_one<BLOCK_N, ACT_GELU>() || init_one<BLOCK_N, ACT_SWIGLU>()) return -2;
+  if constexpr (BLOCK_N >= 128) {
+    if (init_one<BLOCK_N, ACT_ROPE>()) return -2;
+  }
   return 0;
 }
 // Opt every instantiation into its dynamic shared memory size (done once, outside any capture).
@@ -700,6 +785,7 @@ static int init_pair() {
   VCL_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BLOCK_N, ACT_QGELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BLOCK_N>::SMEM_BYTES));
   VCL_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BLOCK_N, ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BLOCK_N>::SMEM_BYTES));
   VCL_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BLOCK_N, ACT_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BLOCK_N>::SMEM_BYTES));
+  VCL_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BLOCK_N, ACT_ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<BLOCK_N>::SMEM_BYTES));
   return 0;
 }
 
@@ -725,6 +811,14 @@ int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
               "gemm: residual must be 16-byte aligned with pitch x8");
   VCL_REQUIRE(g.bias == nullptr || ((uintptr_t)g.bias % 16) == 0, "gemm: bias alignment");
   VCL_REQUIRE(!(g.act == ACT_SWIGLU && g.residual != nullptr), "gemm: swiglu takes no residual");
+  if (g.act == ACT_ROPE) {
+    const RopeEpilogue& r = g.rope;
+    VCL_REQUIRE(r.cos_t && r.sin_t && r.kcache && r.vcache && r.S > 0 && r.H > 0, "gemm: ACT_ROPE needs the RoPE tables and the cache");
+    VCL_REQUIRE(g.N == 3 * r.H * 128 && g.M % r.S == 0 && r.start_pos + r.S <= r.s_max && g.bias == nullptr && g.residual == nullptr,
+                "gemm: ACT_ROPE shape (N=%d, H=%d, M=%d, S=%d, start %d, cache %d)", g.N, r.H, g.M, r.S, r.start_pos, r.s_max);
+    VCL_REQUIRE(((uintptr_t)r.kcache % 16) == 0 && ((uintptr_t)r.vcache % 16) == 0 && ((uintptr_t)r.cos_t % 16) == 0 &&
+                    ((uintptr_t)r.sin_t % 16) == 0, "gemm: ACT_ROPE pointers must be 16-byte aligned");
+  }
   int bn = g.block_n;
   int cl = g.cluster;
   if (bn == 0) {
@@ -758,6 +852,8 @@ int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream) {
     if (forced_cl == 1 && mt >= 2 && mt < 16 && bn == 128 && g.N % 256 == 0 && mt * (g.N / 256) >= sms) bn = 256;
   }
   if (cl == 0) cl = 1;
+  if (g.act == ACT_ROPE && g.block_n == 0 && bn < 128) bn = 128;      // one head (128 columns) per tile at least
+  VCL_REQUIRE(g.act != ACT_ROPE || bn == 128 || bn == 256, "gemm: ACT_ROPE needs 128- or 256-wide tiles (one head = 128 columns), got %d", bn);
   // cluster = -2 (or VCL_GEMM_PAIR=1 for every launch with at least two row tiles): CTA pairs, cta_group::2
   static const bool pair_all = getenv("VCL_GEMM_PAIR") != nullptr;
   if ((cl == -2 || (pair_all && g.M > 128)) && (bn == 256 || bn == 128) && g.N % bn == 0)

@@ -11,7 +11,15 @@ namespace vcl {
 
 typedef __nv_bfloat16 bf16;
 
-enum Act { ACT_NONE = 0, ACT_QGELU = 1, ACT_GELU = 2, ACT_SWIGLU = 3 };
+enum Act { ACT_NONE = 0, ACT_QGELU = 1, ACT_GELU = 2, ACT_SWIGLU = 3, ACT_ROPE = 4 };
+// ACT_ROPE: the GEMM is the LLaMA q|k|v projection of a prefill (N = 3 * H * 128, rows = [clip][position]).
+// The epilogue rotates q and k (RoPE, every product and the sum rounded to bf16 like the reference), writes q to
+// C (columns [0, H * 128)), k and v straight into the KV cache; the k | v columns of C are not written.
+struct RopeEpilogue {
+  const bf16* cos_t = nullptr; const bf16* sin_t = nullptr;    // [s_max][64]
+  bf16* kcache = nullptr; bf16* vcache = nullptr;              // [clip][head][s_max][128] of this layer
+  int S = 0, start_pos = 0, H = 0, s_max = 0;                  // rows per clip, position of row 0, heads
+};
 
 void set_last_error(const char* fmt, ...);
 void count_launches(long long n);
@@ -30,6 +38,7 @@ struct GemmArgs {
   int block_n = 0;     // 0 = choose
   int cluster = 0;     // CTAs per cluster along M sharing multicast weight tiles: 0/1, 2 or 4
   int max_ctas = 0;    // 0 = one per SM
+  RopeEpilogue rope;   // act == ACT_ROPE only
 };
 int launch_gemm_bf16_tn(const GemmArgs& g, cudaStream_t stream);
 int init_gemm_kernels();

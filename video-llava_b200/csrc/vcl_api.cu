@@ -552,9 +552,21 @@ int llm_prefill(vcl_handle* h, const int64_t* ids, const void* video_feats, cons
   for (int l = 0; l < n_layers; ++l) {
     const LlmLayerW& w = h->ll[l];
     VCL_TRY(launch_rmsnorm(h->l_h, D, h->l_x, D, w.ln1, M, D, c.rms_eps, st));
-    VCL_TRY(gemm(h->l_x, D, w.wqkv, D, h->l_qkv, 3 * D, nullptr, nullptr, 0, M, 3 * D, D, ACT_NONE, st));
-    VCL_TRY(launch_rope_kv_prefill(h->l_qkv, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin, B,
-                                   S, H, 128, c.max_seq, start_pos, st));
+    // q|k|v projection with RoPE and the KV-cache write in its epilogue: q lands (rotated) in l_qkv, k and v in
+    // the cache. VCL_PREFILL_ROPE_SEPARATE=1: plain GEMM + rope_kv_prefill_kernel (A/B)
+    static const bool rope_separate = getenv("VCL_PREFILL_ROPE_SEPARATE") != nullptr;
+    if (!rope_separate) {
+      GemmArgs g;
+      g.A = h->l_x; g.lda = D; g.W = w.wqkv; g.ldw = D; g.C = h->l_qkv; g.ldc = 3 * D; g.M = M; g.N = 3 * D; g.K = D;
+      g.act = ACT_ROPE;
+      g.rope.cos_t = h->rope_cos; g.rope.sin_t = h->rope_sin; g.rope.kcache = kc_layer(h, l); g.rope.vcache = vc_layer(h, l);
+      g.rope.S = S; g.rope.start_pos = start_pos; g.rope.H = H; g.rope.s_max = c.max_seq;
+      VCL_TRY(launch_gemm_bf16_tn(g, st));
+    } else {
+      VCL_TRY(gemm(h->l_x, D, w.wqkv, D, h->l_qkv, 3 * D, nullptr, nullptr, 0, M, 3 * D, D, ACT_NONE, st));
+      VCL_TRY(launch_rope_kv_prefill(h->l_qkv, kc_layer(h, l), vc_layer(h, l), h->rope_cos, h->rope_sin, B,
+                                     S, H, 128, c.max_seq, start_pos, st));
+    }
     AttnArgs a;
     a.q = h->l_qkv; a.q_sb = (long long)S * 3 * D; a.q_sh = 128; a.q_ss = 3 * D;
     a.k = kc_layer(h, l); a.k_sb = (long long)H * c.max_seq * 128; a.k_sh = (long long)c.max_seq * 128; a.k_ss = 128;
