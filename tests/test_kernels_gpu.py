@@ -144,6 +144,28 @@ def test_attention(B, S, H, hd, causal):
     assert rel < 6e-3, rel  # P is rounded un-normalised (flash form) vs normalised in eager
 
 
+@pytest.mark.parametrize("B,S,H", [(1, 448, 32), (2, 77, 5), (3, 129, 3), (1, 511, 1), (2, 512, 4), (1, 16, 2)])
+def test_attention_prefill_tcgen05_vs_mma_sync(B, S, H):
+    """The tcgen05 prefill kernel against the flash-style mma.sync kernel it replaces, same inputs, one process
+    (VCL_PREFILL_ATTN_FLASH is read per call): they differ only in where P is rounded (relative to the final row
+    maximum vs the running one), so they agree far inside the tolerance either has against the eager reference."""
+    import os
+    torch.manual_seed(B * 1000 + S + H)
+    dev = _dev()
+    q, k, v = [torch.randn(B, S, H, 128, device=dev).bfloat16() for _ in range(3)]
+    o_tc = vn.op_attention(q, k, v, 128 ** -0.5, True)
+    os.environ["VCL_PREFILL_ATTN_FLASH"] = "1"
+    try:
+        o_mma = vn.op_attention(q, k, v, 128 ** -0.5, True)
+    finally:
+        del os.environ["VCL_PREFILL_ATTN_FLASH"]
+    assert torch.isfinite(o_tc.float()).all()
+    rel = _rel(o_tc, o_mma)
+    per_row = (o_tc.float() - o_mma.float()).flatten(2).norm(dim=2) / o_mma.float().flatten(2).norm(dim=2)
+    assert rel < 4e-3 and per_row.max().item() < 2e-2, (rel, per_row.max().item())
+    assert not torch.equal(o_tc, o_mma) or S <= 16      # two different kernels did run
+
+
 @pytest.mark.parametrize("n,S,H", [(3, 257, 16), (2, 257, 2), (4, 200, 3), (2, 129, 1), (2, 256, 2), (100, 257, 16)])
 def test_attention_vit_tcgen05(n, S, H):
     torch.manual_seed(S + H)

@@ -344,7 +344,8 @@ int init_attention_prefill_tc_kernels() {
 
 // The shapes this kernel takes: causal, head_dim 128, at most 512 keys, 16-byte aligned rows.
 bool attention_prefill_tc_supported(const AttnArgs& a) {
-  static const bool off = getenv("VCL_PREFILL_ATTN_FLASH") != nullptr;     // A/B: the mma.sync kernel
+  const bool off = getenv("VCL_PREFILL_ATTN_FLASH") != nullptr;            // A/B: the mma.sync kernel (read per call, so
+                                                                           // that a test can compare the two in one process)
   const int S_kv = a.S_kv > 0 ? a.S_kv : a.S;
   if (off || !a.causal || a.head_dim != 128 || S_kv > 128 * PA_MAX_KB || a.S <= 0) return false;
   if (a.q_off + a.S > S_kv) return false;                                 // every query sees its own key
