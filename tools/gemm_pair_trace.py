@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "video-llava_b200"))
 import vcl_native as vn
 dev = torch.device("cuda:0")
-M, N, K = 256, 256, 8192
+M, N, K = [int(x) for x in os.environ.get("PAIR_SHAPE", "256,256,8192").split(",")]   # e.g. PAIR_SHAPE=25700,3072,1024
 a = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
 for _ in range(3): vn.op_gemm(a, w, None, None, vn.ACT_NONE, 256, cluster=-2)
 buf = torch.zeros(2 * 128 * 4, dtype=torch.int64, device=dev)
@@ -23,5 +23,11 @@ print(f"pair kernel {s.elapsed_time(e)*1e3:.1f} us for {K//64} k-blocks; single-
 print("kb | leader producer: empty-wait start, ready | peer producer: start, ready | leader MMA: full-wait start, ready   (ns from start)")
 for kb in list(range(0, 24)) + [60, 100, 127]:
     print(kb, t[0, kb, 0] - t0, t[0, kb, 1] - t0, "|", t[1, kb, 0] - t0, t[1, kb, 1] - t0, "|", t[0, kb, 2] - t0, t[0, kb, 3] - t0)
+nk = K // 64
+if nk < 128:
+    print(f"tile boundaries every {nk} k-blocks: ns between consecutive full-barrier completions around them")
+    dd = np.diff(t[0, :128, 3])
+    for b in range(nk, 120, nk):
+        print("  k-block", b, ":", dd[b - 3:b + 3].tolist(), "| MMA waited", (t[0, b, 3] - t[0, b, 2]), "ns for its operands, issue gap to the previous", t[0, b, 2] - t[0, b - 1, 3])
 d = np.diff(t[0, 8:120, 3])
 print("steady state: ns between consecutive full-barrier completions: mean", d.mean(), "p10", np.percentile(d, 10), "p90", np.percentile(d, 90))

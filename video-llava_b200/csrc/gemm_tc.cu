@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(384, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, bf16* C,
                      long long ldc, const bf16* __restrict__ bias, const bf16* residual, long long ldr, int M, int N,
                      int K, int pf_ahead, unsigned long long* __restrict__ trace, const RopeEpilogue rope) {
-  // debug timeline (tools/gemm_pair_trace.py): [cta < 2][k-block < 128][4] globaltimer stamps; null in production
+  // debug timeline (tools/gemm_pair_trace.py): [cta < 2][k-block < 128, counted over the tiles][4] globaltimer stamps; null in production
   auto stamp = [&](int kbi, int ev) {
     if (trace != nullptr && blockIdx.x < 2 && kbi < 128) {
       unsigned long long t_;
@@ -522,13 +522,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
       };
       for (int i = 0; i < pf_ahead; ++i) prefetch_next();
+      int gkb = 0;                                           // k-blocks issued by this CTA so far (trace index)
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int m_blk = (tile / num_n) * 2 + (int)rank, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = 0; kb < num_k; ++kb, ++gkb) {
           if (pf_ahead > 0) prefetch_next();
-          stamp(kb, 0);
+          stamp(gkb, 0);
           mbar_wait_safe(empty_bar(stage), phase ^ 1u);
-          stamp(kb, 1);
+          stamp(gkb, 1);
           const uint32_t lead_full = mapa_cluster(full_bar(stage), 0);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);   // the bytes of BOTH CTAs
           const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
@@ -546,15 +547,16 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int gkb = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         mbar_wait_safe(tempty_bar(acc), acc_phase ^ 1u);     // both epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_k; ++kb) {
-          stamp(kb, 2);
+        for (int kb = 0; kb < num_k; ++kb, ++gkb) {
+          stamp(gkb, 2);
           mbar_wait_safe(full_bar(stage), phase);
           tc_fence_after();
-          stamp(kb, 3);
+          stamp(gkb, 3);
           const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t a_desc = umma_desc_k_sw128(a_addr);
           const uint64_t b_desc = umma_desc_k_sw128(a_addr + Cfg::A_BYTES);
@@ -652,6 +654,11 @@ int device_num_sms() {
 // streams its quarter of a 256-wide weight tile -- gate|up 95 -> 88 us at depth 8, q|k|v 71 -> 65 us (level with
 // the 128-wide tiles it then uses anyway) -- is neutral for the CTA pairs and costs 5-10 % where every row tile
 // prefetches the same weights for itself (no cluster). VCL_GEMM_PF=<k-blocks> overrides (0 = off) for A/B runs.
+// The ACTIVATION operand of the ViT GEMMs was tried too: the per-k-block timeline (tools/gemm_pair_trace.py,
+// PAIR_SHAPE=25700,3072,1024) shows a ~2.9 us bubble at every tile start (the first loads of rows nobody has touched
+// take 2.6-4.4 us against 0.33 us per k-block), yet pulling the next tile's rows into L2 ahead of time made every
+// shape SLOWER, through the TMA (q|k|v 132 -> 144 us, fc2 153 -> 188) as well as with plain prefetch.global.L2
+// issued by the idle warp (128 -> 143, 153 -> 172). Not kept.
 static int weight_prefetch_depth(const GemmArgs& g, int block_n, int cl) {
   static const int forced = getenv("VCL_GEMM_PF") ? atoi(getenv("VCL_GEMM_PF")) : -1;
   if (forced >= 0) return forced;
