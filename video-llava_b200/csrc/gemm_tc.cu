@@ -69,7 +69,7 @@ __device__ __forceinline__ float act_silu(float g) {
 template <int BLOCK_N, class WaitFn, class ArriveFn>
 __device__ __forceinline__ void gemm_epilogue_rope(uint32_t tmem_acc, int q4, int hf, int lane, int m_blk, int n_blk,
                                                    bf16* C, long long ldc, int M, const RopeEpilogue& rp,
-                                                   WaitFn wait_full, ArriveFn arrive_empty) {
+                                                   uint8_t* stg, WaitFn wait_full, ArriveFn arrive_empty) {
   if constexpr (BLOCK_N == 128 || BLOCK_N == 256) {
     constexpr int UNITS = BLOCK_N / 128;
     const int row = m_blk * 128 + q4 * 32 + lane;
@@ -88,44 +88,65 @@ __device__ __forceinline__ void gemm_epilogue_rope(uint32_t tmem_acc, int q4, in
       tmem_ld_32x32(tl + hh * 128 + 64 + d0, hi);
       tc_wait_ld();
       if (u == UNITS - 1) arrive_empty();                     // every TMEM read of this accumulator has completed
-      if (row_ok) {
-        const int gh = n_blk * UNITS + hh;                    // head index over q | k | v
-        const int which = gh / rp.H, head = gh - which * rp.H;
-        const long long coff = (((long long)b * rp.H + head) * rp.s_max + pos) * 128 + d0;
-        uint32_t olo[16], ohi[16];
-        if (which == 2) {
+      const int gh = n_blk * UNITS + hh;                      // head index over q | k | v (the same for the warp)
+      const int which = gh / rp.H, head = gh - which * rp.H;
+      uint32_t olo[16], ohi[16];
+      if (row_ok && which == 2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            olo[j] = pack_bf16x2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
-            ohi[j] = pack_bf16x2(__uint_as_float(hi[2 * j]), __uint_as_float(hi[2 * j + 1]));
-          }
-        } else {
-          const bf16* ct = rp.cos_t + (long long)pos * 64 + d0;
-          const bf16* st = rp.sin_t + (long long)pos * 64 + d0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(ct + q * 8));
-            const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(st + q * 8));
-            const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w}, sw[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = q * 4 + e;                        // pair of columns 2j, 2j + 1
-              const uint32_t l2 = pack_bf16x2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
-              const uint32_t h2 = pack_bf16x2(__uint_as_float(hi[2 * j]), __uint_as_float(hi[2 * j + 1]));
-              const float l0 = bf16lo(l2), l1 = bf16hi(l2), h0 = bf16lo(h2), h1 = bf16hi(h2);
-              const float c0 = bf16lo(cw[e]), c1 = bf16hi(cw[e]), s0 = bf16lo(sw[e]), s1 = bf16hi(sw[e]);
-              olo[j] = pack_bf16x2(bf16r(l0 * c0) + bf16r(-h0 * s0), bf16r(l1 * c1) + bf16r(-h1 * s1));
-              ohi[j] = pack_bf16x2(bf16r(h0 * c0) + bf16r(l0 * s0), bf16r(h1 * c1) + bf16r(l1 * s1));
-            }
-          }
+        for (int j = 0; j < 16; ++j) {
+          olo[j] = pack_bf16x2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
+          ohi[j] = pack_bf16x2(__uint_as_float(hi[2 * j]), __uint_as_float(hi[2 * j + 1]));
         }
-        bf16* dst = which == 0 ? C + (long long)row * ldc + gh * 128 + d0
-                               : (which == 1 ? rp.kcache : rp.vcache) + coff;
+      } else if (row_ok) {
+        const bf16* ct = rp.cos_t + (long long)pos * 64 + d0;
+        const bf16* st = rp.sin_t + (long long)pos * 64 + d0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          *reinterpret_cast<uint4*>(dst + q * 8) = make_uint4(olo[4 * q], olo[4 * q + 1], olo[4 * q + 2], olo[4 * q + 3]);
-          *reinterpret_cast<uint4*>(dst + 64 + q * 8) = make_uint4(ohi[4 * q], ohi[4 * q + 1], ohi[4 * q + 2], ohi[4 * q + 3]);
+          const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(ct + q * 8));
+          const uint4 s4 = __ldg(reinterpret_cast<const uint4*>(st + q * 8));
+          const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w}, sw[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = q * 4 + e;                        // pair of columns 2j, 2j + 1
+            const uint32_t l2 = pack_bf16x2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
+            const uint32_t h2 = pack_bf16x2(__uint_as_float(hi[2 * j]), __uint_as_float(hi[2 * j + 1]));
+            const float l0 = bf16lo(l2), l1 = bf16hi(l2), h0 = bf16lo(h2), h1 = bf16hi(h2);
+            const float c0 = bf16lo(cw[e]), c1 = bf16hi(cw[e]), s0 = bf16lo(sw[e]), s1 = bf16hi(sw[e]);
+            olo[j] = pack_bf16x2(bf16r(l0 * c0) + bf16r(-h0 * s0), bf16r(l1 * c1) + bf16r(-h1 * s1));
+            ohi[j] = pack_bf16x2(bf16r(h0 * c0) + bf16r(l0 * s0), bf16r(h1 * c1) + bf16r(l1 * s1));
+          }
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { olo[j] = 0u; ohi[j] = 0u; }
+      }
+      // both 64-byte halves of the row leave through the warp's staging block (gemm_epilogue_tile): 8 rows x 64
+      // contiguous bytes per store instruction; the destination row is recomputed for the row a lane stores
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int swz = (lane >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t* src = half == 0 ? olo : ohi;
+          *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ swz) << 4)) =
+              make_uint4(src[4 * q], src[4 * q + 1], src[4 * q + 2], src[4 * q + 3]);
+        }
+        __syncwarp();
+        const int r0 = lane >> 2, cc = lane & 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = 8 * k + r0;
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4));
+          const int grow = m_blk * 128 + q4 * 32 + r;
+          if (grow < M) {
+            const int gb = grow / rp.S, gs = grow - gb * rp.S;
+            bf16* dst = which == 0
+                ? C + (long long)grow * ldc + gh * 128 + d0
+                : (which == 1 ? rp.kcache : rp.vcache) + (((long long)gb * rp.H + head) * rp.s_max + rp.start_pos + gs) * 128 + d0;
+            *reinterpret_cast<uint4*>(dst + half * 64 + cc * 8) = val;
+          }
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -146,7 +167,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t tmem_acc, int q4, in
                                                    const RopeEpilogue& rope, uint8_t* stg, WaitFn wait_full,
                                                    ArriveFn arrive_empty) {
   if constexpr (ACT == ACT_ROPE) {
-    gemm_epilogue_rope<BLOCK_N>(tmem_acc, q4, hf, lane, m_blk, n_blk, C, ldc, M, rope, wait_full, arrive_empty);
+    gemm_epilogue_rope<BLOCK_N>(tmem_acc, q4, hf, lane, m_blk, n_blk, C, ldc, M, rope, stg, wait_full, arrive_empty);
     return;
   }
   constexpr int CH = BLOCK_N / 32;
@@ -203,23 +224,39 @@ __device__ __forceinline__ void gemm_epilogue_tile(uint32_t tmem_acc, int q4, in
         }
       };
       if constexpr (ACT == ACT_SWIGLU) {
-        if (row_ok && col0 < N) {
-          float f[32];
-          load_f(f);
-          // weight rows are interleaved (2j = gate_j, 2j+1 = up_j): 32 columns -> 16 outputs
+        if (col0 < N) {                            // warp-uniform
+          // weight rows are interleaved (2j = gate_j, 2j+1 = up_j): 32 columns -> 16 outputs (32 bytes per row)
           uint32_t o[8];
+          if (row_ok) {
+            float f[32];
+            load_f(f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t g2 = pack_bf16x2(f[4 * j + 0], f[4 * j + 2]);   // gate pair (bf16)
-            const uint32_t u2 = pack_bf16x2(f[4 * j + 1], f[4 * j + 3]);   // up pair (bf16)
-            const float g0 = bf16lo(g2), g1 = bf16hi(g2);
-            const uint32_t s2 = pack_bf16x2(__fdividef(g0, 1.0f + __expf(-g0)),
-                                            __fdividef(g1, 1.0f + __expf(-g1)));   // silu (bf16)
-            o[j] = bf16x2_mul(s2, u2);
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t g2 = pack_bf16x2(f[4 * j + 0], f[4 * j + 2]);   // gate pair (bf16)
+              const uint32_t u2 = pack_bf16x2(f[4 * j + 1], f[4 * j + 3]);   // up pair (bf16)
+              const float g0 = bf16lo(g2), g1 = bf16hi(g2);
+              const uint32_t s2 = pack_bf16x2(__fdividef(g0, 1.0f + __expf(-g0)),
+                                              __fdividef(g1, 1.0f + __expf(-g1)));   // silu (bf16)
+              o[j] = bf16x2_mul(s2, u2);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0u;
           }
-          bf16* dst = C + (long long)row * ldc + (col0 >> 1);
-          *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+          // staged like the plain path below: 16 rows x 32 contiguous bytes (one sector each) per instruction
+          const int sw = (lane >> 2) & 1;
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((0 ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((1 ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+          __syncwarp();
+          const int r0 = lane >> 1, cc = lane & 1;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int r = 16 * k + r0;
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 32 + ((cc ^ ((r >> 2) & 1)) << 4));
+            const int grow = m_blk * 128 + q4 * 32 + r;
+            if (grow < M) *reinterpret_cast<uint4*>(C + (long long)grow * ldc + (col0 >> 1) + cc * 8) = val;
+          }
+          __syncwarp();
         }
       } else if (col0 < N) {                       // warp-uniform: every lane takes part in the staged store
         uint32_t o[16];
