@@ -8,8 +8,10 @@
 //   warp 1      MMA issuer   : one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per stage
 //   warp 2      TMEM allocator (2 accumulator buffers of BLOCK_N fp32 columns)
 //   warps 4-11  epilogue     : tcgen05.ld 32 lanes x 32 columns -> bias / activation / residual
-//                              -> bf16 -> global (64 B contiguous per thread per chunk); two warps
-//                              per TMEM lane quarter, software-pipelined over the column chunks
+//                              -> bf16 -> a 2 KB per-warp staging block in shared memory (a thread owns
+//                              64 contiguous bytes of ONE row; the block is read back transposed so that
+//                              a store instruction writes 8 rows x 64 contiguous bytes) -> global; two
+//                              warps per TMEM lane quarter, software-pipelined over the column chunks
 //
 // Persistent: grid = min(#tiles, #SMs); the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the mainloop of tile i+1.
@@ -20,6 +22,8 @@
 //   CLIP residual    hidden + out        transformers/models/clip/modeling_clip.py:377,382
 //   LLaMA SwiGLU     silu(gate)*up       transformers/models/llama/modeling_llama.py:182-184
 //   LLaMA residual                       transformers/models/llama/modeling_llama.py:325,331
+//   LLaMA RoPE + KV-cache write (ACT_ROPE, the prefill's q|k|v projection)
+//                                        transformers/models/llama/modeling_llama.py:124-168
 #include "common.cuh"
 #include "kernels.h"
 
